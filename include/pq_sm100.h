@@ -1,0 +1,123 @@
+/*
+ * pq_sm100.h -- C ABI of libpq_sm100.so, the B200 (sm_100a) kernels behind the
+ * calibration + simulation hot path of pytorch-quantity.
+ *
+ * The reference has no FFI: its operator API is plain Python classes over numpy / torch
+ * (SURVEY.md 8b).  Each entry point below therefore names the reference Python function
+ * whose arithmetic it replaces (paths relative to /root/reference/quantity/); the Python
+ * classes of the same names in pytorch-quantity_b200/common/quantity/ bind these symbols
+ * through ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in _host.  The caller (PyTorch) owns every buffer including
+ *     workspaces; the library allocates nothing and keeps no state besides cached
+ *     function attributes / TMA descriptors.
+ *   - all work is enqueued on `stream` (a cudaStream_t); no call synchronises.
+ *   - return 0 on success, a negative PQ_E* for bad arguments / unsupported shapes, or a
+ *     positive cudaError_t.  Nothing throws or aborts across the ABI.  There is no CPU
+ *     fallback: an unsupported request is an error the Python side raises.
+ *   - accumulating entry points (absmax, hist) combine with atomics, so successive
+ *     batches, several streams and several tensors compose; results are independent of
+ *     launch order (unsigned max / integer add), which is what makes the multi-GPU
+ *     merge (NCCL MAX / SUM on the same buffers) bit-exact.
+ */
+#ifndef PQ_SM100_H
+#define PQ_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *pq_stream_t; /* cudaStream_t */
+
+#define PQ_OK 0
+#define PQ_EINVAL (-1)       /* null pointer, negative size, bad enum */
+#define PQ_EUNSUPPORTED (-2) /* shape / alignment the kernels do not implement */
+#define PQ_EALIGN (-3)       /* pointer not aligned as documented */
+#define PQ_ETOOMANY (-4)     /* more segments than PQ_MAX_SEGMENTS in one call */
+
+#define PQ_HIST_BINS 2048   /* tools/configs.yml:23 INTERVAL_NUM */
+#define PQ_KL_TARGET_BIN 128 /* common/quantity/quantizer.py:98 target_bin */
+#define PQ_KL_CANDIDATES (PQ_HIST_BINS - PQ_KL_TARGET_BIN)
+#define PQ_MAX_SEGMENTS 256 /* tensors per multi-tensor launch */
+
+int pq_version(void);
+const char *pq_error_string(int code);
+
+/* ---- a1: DistributionCollector.refresh_max_val, common/quantity/distribution_collector.py:70-78
+ * max_bits[i] = max(max_bits[i], bits(|x|)) over tensor i, as the uint32 pattern of the
+ * fp32 magnitude (monotone for non-NaN floats; reinterpret as float to read it).
+ * xs_host / ns_host are HOST arrays of k device pointers / element counts. */
+int pq_absmax_multi_f32(const float *const *xs_host, const uint64_t *ns_host, int k,
+                        uint32_t *max_bits, pq_stream_t stream);
+
+/* ---- a3: DistributionCollector._add_to_distribution, distribution_collector.py:127-135
+ * for every x != 0:  hist[i][min((int)trunc(fl32(|x| / interval_i)), 2047)] += 1
+ * with a correctly rounded fp32 division.  hist is int64 [k][2048] (the reference's int32
+ * would overflow at BASELINE.json's 8192-image config; the Python layer narrows to int32
+ * when it fits).  intervals_host: HOST array of k fp32 bin widths (a2, :60-61). */
+int pq_hist2048_multi_f32(const float *const *xs_host, const uint64_t *ns_host,
+                          const float *intervals_host, int k, long long *hist,
+                          pq_stream_t stream);
+
+/* ---- a5 + a6: Quantizer.normalize_distribution / threshold_distribution /
+ * compute_kl_divergence, common/quantity/quantizer.py:95-174
+ * counts: fp64 [k][2048] (integer-valued: int32 counts or the float64 group sums of
+ * tools/pytorch_quantizer.py:434-445).  Outputs: threshold[k] (the chosen bin T*, first
+ * strict minimum, default 2047) and, if kl != NULL, kl[k][1920] (the divergences for
+ * T = 128..2047).  workspace: fp64 [k][pq_kl_workspace_doubles()] scratch.
+ * All arithmetic in fp64 in the reference's operation order (numpy pairwise sums
+ * included); only log() differs from numpy's by <= 1 ulp. */
+size_t pq_kl_workspace_doubles(void);
+int pq_kl_search_f64(const double *counts, int k, double *workspace, double *kl,
+                     int *threshold, pq_stream_t stream);
+
+/* ---- a10 / a12: QuanDequan.forward (new_quantity_op.py:246-257) and Quantity.forward (:48-58)
+ * y = clamp(rint_half_even(x * 2^bit), lo, hi) [/ 2^bit when dequant != 0].  y may alias x. */
+int pq_fakequant_f32(const float *x, float *y, size_t n, int bit, float lo, float hi,
+                     int dequant, pq_stream_t stream);
+
+/* ---- a15: NewAdd.forward, new_quantity_op.py:166-174:  y = clamp(a + b, lo, hi). */
+int pq_add_clamp_f32(const float *a, const float *b, float *y, size_t n, float lo, float hi,
+                     pq_stream_t stream);
+
+/* ---- a12 (layout-changing form): Quantity.forward fused with the NCHW -> NHWC transpose
+ * the tensor-core kernels want:  q[n][h][w][c_pad] = (int8) clamp(rint(x[n][c][h][w] * 2^ib)).
+ * Channels c >= C of the padded layout are written as 0. */
+int pq_quantize_nchw_to_nhwc_s8(const float *x, int8_t *q, int N, int C, int H, int W, int c_pad,
+                                int ib, pq_stream_t stream);
+
+/* ---- a13 + a14: NewConv2d.forward / NewLinear.forward, new_quantity_op.py:104-133,177-205
+ * (Conv -> RightShift -> BiasAdd -> Sp -> DeQuantity) on int8 operands:
+ *   acc  = sum_k a[m][k] * w[n][k]                 int8 x int8 -> int32 (tcgen05 kind::i8)
+ *   r    = clamp(round_half_away(acc / 2^rs), -128, 127)              (RightShift, :11-44)
+ *   y    = clamp(r + bias_q[n], -128, 127)                            (BiasAdd + Sp, :71-101)
+ *   out  = y / 2^ob                                                   (DeQuantity, :61-68)
+ * pq_gemm_s8: a is [M][K] row-major int8 (NHWC activations of a 1x1/stride-1 conv, or the
+ * input of a Linear), w is [N][K] row-major int8, K % 16 == 0, 16-byte aligned rows.
+ * Outputs (either may be NULL): out_f32 written as NCHW fp32 with `hw` pixels per image
+ * (hw = 1 gives the plain [M][N] row-major layout of a Linear); out_s8 written [M][N]. */
+typedef struct pq_conv_desc {
+    int N, H, W, C;          /* input NHWC, C = padded channel count (multiple of 16) */
+    int K;                   /* output channels */
+    int R, S;                /* filter height / width; weights are [K][R][S][C] int8 */
+    int stride_h, stride_w, pad_h, pad_w;
+    int P, Q;                /* output height / width */
+    int rs;                  /* weight_bit + input_bit - output_bit, any sign */
+    int ob;                  /* output_bit */
+} pq_conv_desc;
+
+int pq_gemm_s8(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K,
+               int rs, int ob, int hw, float *out_f32, int8_t *out_s8, pq_stream_t stream);
+int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
+                 const pq_conv_desc *desc_host, float *out_f32_nchw, int8_t *out_s8_nhwc,
+                 pq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQ_SM100_H */
