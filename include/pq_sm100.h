@@ -77,13 +77,25 @@ int pq_kl_search_f64(const double *counts, int k, double *workspace, double *kl,
                      int *threshold, pq_stream_t stream);
 
 /* ---- a10 / a12: QuanDequan.forward (new_quantity_op.py:246-257) and Quantity.forward (:48-58)
- * y = clamp(rint_half_even(x * 2^bit), lo, hi) [/ 2^bit when dequant != 0].  y may alias x. */
+ * y = clamp(rint_half_even(x * 2^bit), lo, hi) [/ 2^bit when dequant != 0].  y must not alias x
+ * (inputs are read through the non-coherent path). */
 int pq_fakequant_f32(const float *x, float *y, size_t n, int bit, float lo, float hi,
                      int dequant, pq_stream_t stream);
 
 /* ---- a15: NewAdd.forward, new_quantity_op.py:166-174:  y = clamp(a + b, lo, hi). */
 int pq_add_clamp_f32(const float *a, const float *b, float *y, size_t n, float lo, float hi,
                      pq_stream_t stream);
+
+/* ---- a14 stand-alone: RightShift.forward, new_quantity_op.py:11-44 on fp32 tensors
+ * v = x / 2^rs (rs any sign); r = trunc(v + 0.5) if v > 0 else trunc(v - 0.5); y = clamp(r, lo, hi).
+ * (Inside NewConv2d / NewLinear this is fused into the GEMM epilogue; this entry serves the
+ * module when it is used on its own.) */
+int pq_rshift_f32(const float *x, float *y, size_t n, int rs, float lo, float hi, pq_stream_t stream);
+
+/* ---- Sp.forward (:71-91) and DeQuantity.forward (:61-68) stand-alone:
+ * y = clamp(x, lo, hi) * scale  (Sp: scale = 1; DeQuantity: lo/hi = -/+inf, scale = 2^-ob). */
+int pq_clamp_scale_f32(const float *x, float *y, size_t n, float lo, float hi, float scale,
+                       pq_stream_t stream);
 
 /* ---- a12 (layout-changing form): Quantity.forward fused with the NCHW -> NHWC transpose
  * the tensor-core kernels want:  q[n][h][w][c_pad] = (int8) clamp(rint(x[n][c][h][w] * 2^ib)).

@@ -1,0 +1,258 @@
+"""ctypes binding of libpq_sm100.so (the C ABI declared in include/pq_sm100.h).
+
+PyTorch supplies device memory and streams; every kernel on the calibration / simulation
+hot path is one of the hand-written sm_100a kernels behind these symbols.  There is no CPU
+or eager fallback: if the library is missing, or a tensor is not on a CUDA device, the
+call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libpq_sm100.so")
+
+HIST_BINS = 2048
+KL_TARGET_BIN = 128
+KL_CANDIDATES = HIST_BINS - KL_TARGET_BIN
+MAX_SEGMENTS = 256
+
+# every symbol include/pq_sm100.h declares: (restype, argtypes)
+_vp, _i, _sz, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float
+SYMBOLS = {
+    "pq_version": (_i, []),
+    "pq_error_string": (ctypes.c_char_p, [_i]),
+    "pq_absmax_multi_f32": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "pq_hist2048_multi_f32": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "pq_kl_workspace_doubles": (_sz, []),
+    "pq_kl_search_f64": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "pq_fakequant_f32": (_i, [_vp, _vp, _sz, _i, _f, _f, _i, _vp]),
+    "pq_add_clamp_f32": (_i, [_vp, _vp, _vp, _sz, _f, _f, _vp]),
+    "pq_rshift_f32": (_i, [_vp, _vp, _sz, _i, _f, _f, _vp]),
+    "pq_clamp_scale_f32": (_i, [_vp, _vp, _sz, _f, _f, _f, _vp]),
+    "pq_quantize_nchw_to_nhwc_s8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pq_gemm_s8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pq_conv2d_s8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+
+class ConvDesc(ctypes.Structure):
+    """struct pq_conv_desc"""
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("N", "H", "W", "C", "K", "R", "S", "stride_h", "stride_w", "pad_h", "pad_w",
+                 "P", "Q", "rs", "ob")]
+
+
+_lib = None
+
+# ---- instrumentation used by bench.py: launch counts always; CUDA-event timing of each launch
+# on its launching stream when a profile dict is installed with set_profile().
+LAUNCHES = {"total": 0}
+_profile = None
+
+
+def set_profile(store):
+    """store: None (off) or a dict; every C-ABI launch appends (start_evt, end_evt, alg_bytes)
+    to store[kernel_name]."""
+    global _profile
+    _profile = store
+
+
+class _Timed:
+    def __init__(self, name, kernels, alg_bytes, device):
+        self.name, self.kernels, self.alg_bytes, self.device = name, kernels, alg_bytes, device
+
+    def __enter__(self):
+        LAUNCHES["total"] += self.kernels
+        LAUNCHES[self.name] = LAUNCHES.get(self.name, 0) + self.kernels
+        if _profile is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if _profile is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record(torch.cuda.current_stream(self.device))
+            _profile.setdefault(self.name, []).append((self.start, end, self.alg_bytes))
+        return False
+
+
+def lib():
+    """Load the library once.  Raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libpq_sm100.so not found at %s -- build it with `python __graft_entry__.py` "
+                "(or `make -C pytorch-quantity_b200/csrc`).  This package has no CPU fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed: %s (code %d)" % (what, lib().pq_error_string(rc).decode(), rc))
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def require_cuda(t, what):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s needs a CUDA tensor: the B200 path has no CPU fallback" % what)
+
+
+def to_device_f32(x, device=None):
+    """Accept CUDA tensors (fast path) or numpy / CPU tensors (compatibility path: one
+    host->device copy, then the same kernels).  Returns a contiguous 1-D fp32 CUDA tensor."""
+    if isinstance(x, torch.Tensor):
+        t = x.detach()
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
+    if not t.is_cuda:
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device: pytorch-quantity_b200 has no CPU fallback")
+        t = t.to(device or "cuda", non_blocking=True)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous().view(-1)
+
+
+def _seg_arrays(tensors):
+    k = len(tensors)
+    ptrs = (ctypes.c_void_p * k)(*[t.data_ptr() if t.numel() else 0 for t in tensors])
+    ns = (ctypes.c_uint64 * k)(*[t.numel() for t in tensors])
+    return ptrs, ns
+
+
+def absmax_multi(tensors, max_bits):
+    """max_bits (int32 CUDA [>=k], bit patterns of fp32 magnitudes) |= max over each tensor."""
+    for lo in range(0, len(tensors), MAX_SEGMENTS):
+        part = tensors[lo:lo + MAX_SEGMENTS]
+        ptrs, ns = _seg_arrays(part)
+        out = max_bits[lo:lo + len(part)]
+        with _Timed("absmax", 1, 4 * sum(t.numel() for t in part), max_bits.device):
+            check(lib().pq_absmax_multi_f32(ptrs, ns, len(part), out.data_ptr(), _stream(max_bits)),
+                  "pq_absmax_multi_f32")
+
+
+def hist_multi(tensors, intervals, hist):
+    """hist (int64 CUDA [k][2048]) += 2048-bin |x| histograms with per-tensor fp32 bin width."""
+    for lo in range(0, len(tensors), MAX_SEGMENTS):
+        part = tensors[lo:lo + MAX_SEGMENTS]
+        ptrs, ns = _seg_arrays(part)
+        iv = (ctypes.c_float * len(part))(*[float(v) for v in intervals[lo:lo + len(part)]])
+        out = hist[lo:lo + len(part)]
+        with _Timed("hist", 1, 4 * sum(t.numel() for t in part), hist.device):
+            check(lib().pq_hist2048_multi_f32(ptrs, ns, iv, len(part), out.data_ptr(), _stream(hist)),
+                  "pq_hist2048_multi_f32")
+
+
+def kl_search(counts_f64, want_curves=False):
+    """counts_f64: CUDA fp64 [k][2048].  Returns (threshold int32 [k], kl fp64 [k][1920] or None)."""
+    require_cuda(counts_f64, "kl_search")
+    assert counts_f64.dtype == torch.float64 and counts_f64.dim() == 2 and counts_f64.shape[1] == HIST_BINS
+    counts_f64 = counts_f64.contiguous()
+    k = counts_f64.shape[0]
+    dev = counts_f64.device
+    ws = torch.empty(k * lib().pq_kl_workspace_doubles(), dtype=torch.float64, device=dev)
+    thr = torch.empty(k, dtype=torch.int32, device=dev)
+    kl = torch.empty((k, KL_CANDIDATES), dtype=torch.float64, device=dev) if want_curves else None
+    with _Timed("kl", 3, 8 * counts_f64.numel(), dev):
+        check(lib().pq_kl_search_f64(counts_f64.data_ptr(), k, ws.data_ptr(),
+                                     kl.data_ptr() if want_curves else None, thr.data_ptr(),
+                                     _stream(counts_f64)), "pq_kl_search_f64")
+    return thr, kl
+
+
+def _flat_out(x):
+    require_cuda(x, "elementwise kernel")
+    if x.dtype != torch.float32:
+        raise RuntimeError("fp32 expected, got %s" % x.dtype)
+    xc = x.contiguous()
+    return xc, torch.empty_like(xc)
+
+
+def fakequant(x, bit, lo=-128.0, hi=127.0, dequant=True):
+    xc, y = _flat_out(x)
+    with _Timed("fakequant", 1, 8 * xc.numel(), xc.device):
+        check(lib().pq_fakequant_f32(xc.data_ptr(), y.data_ptr(), xc.numel(), int(bit), lo, hi,
+                                     1 if dequant else 0, _stream(xc)), "pq_fakequant_f32")
+    return y
+
+
+def add_clamp(a, b, lo=-128.0, hi=127.0):
+    require_cuda(b, "add_clamp")
+    if a.shape != b.shape:
+        a, b = torch.broadcast_tensors(a, b)
+    ac, y = _flat_out(a)
+    bc = b.contiguous()
+    check(lib().pq_add_clamp_f32(ac.data_ptr(), bc.data_ptr(), y.data_ptr(), ac.numel(), lo, hi,
+                                 _stream(ac)), "pq_add_clamp_f32")
+    return y
+
+
+def rshift(x, rs, lo=-128.0, hi=127.0):
+    xc, y = _flat_out(x)
+    check(lib().pq_rshift_f32(xc.data_ptr(), y.data_ptr(), xc.numel(), int(rs), lo, hi, _stream(xc)),
+          "pq_rshift_f32")
+    return y
+
+
+def clamp_scale(x, lo, hi, scale):
+    xc, y = _flat_out(x)
+    check(lib().pq_clamp_scale_f32(xc.data_ptr(), y.data_ptr(), xc.numel(), lo, hi, scale, _stream(xc)),
+          "pq_clamp_scale_f32")
+    return y
+
+
+def quantize_nchw_to_nhwc_s8(x, ib, c_pad):
+    require_cuda(x, "quantize_nchw_to_nhwc_s8")
+    assert x.dim() == 4 and x.dtype == torch.float32
+    xc = x.contiguous()
+    N, C, H, W = xc.shape
+    q = torch.empty((N, H, W, c_pad), dtype=torch.int8, device=x.device)
+    check(lib().pq_quantize_nchw_to_nhwc_s8(xc.data_ptr(), q.data_ptr(), N, C, H, W, c_pad, int(ib),
+                                            _stream(xc)), "pq_quantize_nchw_to_nhwc_s8")
+    return q
+
+
+def gemm_s8(a, w, bias_q, rs, ob, hw=1, want_f32=True, want_s8=False):
+    """a int8 [M][K], w int8 [N][K], bias_q int32 [N] -> fp32 (NCHW with hw pixels per image,
+    or [M][N] when hw == 1) and / or int8 [M][N]."""
+    require_cuda(a, "gemm_s8")
+    M, K = a.shape
+    N = w.shape[0]
+    out_f32 = out_s8 = None
+    if want_f32:
+        out_f32 = torch.empty((M // hw, N, hw) if hw > 1 else (M, N), dtype=torch.float32, device=a.device)
+    if want_s8:
+        out_s8 = torch.empty((M, N), dtype=torch.int8, device=a.device)
+    check(lib().pq_gemm_s8(a.data_ptr(), w.data_ptr(), bias_q.data_ptr(), M, N, K, int(rs), int(ob), hw,
+                           out_f32.data_ptr() if want_f32 else None,
+                           out_s8.data_ptr() if want_s8 else None, _stream(a)), "pq_gemm_s8")
+    return out_f32, out_s8
+
+
+def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, want_s8=False):
+    require_cuda(x_nhwc, "conv2d_s8")
+    N, H, W, C = x_nhwc.shape
+    K, R, S, C2 = w_krsc.shape
+    assert C == C2
+    P = (H + 2 * padding[0] - R) // stride[0] + 1
+    Q = (W + 2 * padding[1] - S) // stride[1] + 1
+    d = ConvDesc(N, H, W, C, K, R, S, stride[0], stride[1], padding[0], padding[1], P, Q, int(rs), int(ob))
+    out_f32 = torch.empty((N, K, P, Q), dtype=torch.float32, device=x_nhwc.device) if want_f32 else None
+    out_s8 = torch.empty((N, P, Q, K), dtype=torch.int8, device=x_nhwc.device) if want_s8 else None
+    check(lib().pq_conv2d_s8(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
+                             out_f32.data_ptr() if want_f32 else None,
+                             out_s8.data_ptr() if want_s8 else None, _stream(x_nhwc)), "pq_conv2d_s8")
+    return out_f32, out_s8

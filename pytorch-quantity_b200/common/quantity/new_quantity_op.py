@@ -1,0 +1,310 @@
+"""Simulation operators (subsystems 3 and 4) with the reference's constructor signatures and
+attribute names (quantity/common/quantity/new_quantity_op.py:8-452), executed by the sm_100a
+kernels of libpq_sm100.so.
+
+Integer simulation (``ReconModel``): ``NewConv2d`` / ``NewLinear`` run
+  Quantity -> Conv/Linear -> RightShift -> BiasAdd -> Sp -> DeQuantity          (:124-133, :197-205)
+as: one quantise kernel (fp32 NCHW -> int8 NHWC) + one tcgen05 int8 GEMM / implicit-GEMM
+kernel whose epilogue does shift / round-half-away / saturate / bias / saturate / dequantise
+and writes the fp32 NCHW tensor the module API promises.  The stand-alone modules
+(``Quantity``, ``RightShift``, ``Sp``, ``BiasAdd``, ``DeQuantity``) keep working on their own
+through small bandwidth kernels.
+
+Fake-quant simulation (``ReconTest``): ``TestConv`` / ``TestLinear`` fake-quantise weight and
+bias once with ``QuanDequan`` and apply ``QuanDequan`` to the layer output (:259-292, :358-389);
+the fp32 convolution itself stays the user's cuDNN library call, as in the reference.
+
+Deliberate deviations (all documented in INTEGRATION.md):
+  * ``quantized_bias`` is a registered buffer so ``model.cuda()`` moves it (reference quirk Q5);
+  * ``TestConv`` / ``TestLinear`` write their text / PNG diagnostics only when the module-level
+    switch ``WRITE_DIAGNOSTICS`` is on (they cost 25 s per ResNet-18 in the reference);
+  * a missing bias is handled (reference quirk Q6 dereferences a non-existent attribute);
+  * 8-bit only (the 16-bit branches of the reference are inconsistent, quirk Q11).
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native
+
+QUANTIZE_BIT = 8                     # new_quantity_op.py:8
+WRITE_DIAGNOSTICS = False
+
+
+def _range(bits):
+    assert bits == 8 or bits == 16, "Not support bit width."
+    return (-128.0, 127.0) if bits == 8 else (-32768.0, 32767.0)
+
+
+class RightShift(nn.Module):
+    """acc / 2^rs, round half away from zero, saturate (new_quantity_op.py:11-44)."""
+
+    def __init__(self, bits, rs):
+        super().__init__()
+        self.rs = rs
+        self.Bit_width = bits
+
+    def forward(self, x):
+        lo, hi = _range(self.Bit_width)
+        return _native.rshift(x, self.rs, lo, hi).view(x.shape)
+
+
+class Quantity(nn.Module):
+    """clamp(round_half_even(x * 2^ib)) -> integer-valued fp32 (new_quantity_op.py:48-58)."""
+
+    def __init__(self, ib):
+        super().__init__()
+        self.ib = ib
+
+    def forward(self, x):
+        lo, hi = _range(QUANTIZE_BIT)
+        return _native.fakequant(x, self.ib, lo, hi, dequant=False).view(x.shape)
+
+
+class DeQuantity(nn.Module):
+    """x / 2^ob (new_quantity_op.py:61-68)."""
+
+    def __init__(self, ob):
+        super().__init__()
+        self.ob = ob
+
+    def forward(self, x):
+        return _native.clamp_scale(x, float("-inf"), float("inf"), 2.0 ** -self.ob).view(x.shape)
+
+
+class Sp(nn.Module):
+    """Saturating truncation (new_quantity_op.py:71-91)."""
+
+    def __init__(self, bits):
+        super().__init__()
+        self.bitwidth = bits
+
+    def forward(self, x):
+        lo, hi = _range(self.bitwidth)
+        return _native.clamp_scale(x, lo, hi, 1.0).view(x.shape)
+
+
+class BiasAdd(nn.Module):
+    """Plain broadcast add (new_quantity_op.py:95-101); fused into the GEMM epilogue inside
+    NewConv2d / NewLinear."""
+
+    def forward(self, x, y):
+        return torch.add(x, y)
+
+
+def _quantize_param(p, bit):
+    """clamp(round(p * 2^bit), -128, 127) as int8 (new_quantity_op.py:147-152)."""
+    return _native.fakequant(p.detach().float().contiguous(), bit, -128.0, 127.0, dequant=False)
+
+
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+class _IntSimBase(nn.Module):
+    def _read_info(self, quantize_infor):
+        self.weight_bit = quantize_infor["weight_bit"]
+        self.bias_bit = quantize_infor["bias_bit"]
+        self.input_bit = quantize_infor["input_bit"]
+        self.output_bit = quantize_infor["output_bit"]
+        self.rs_bit = self.weight_bit + self.input_bit - self.output_bit
+        self.Quan = Quantity(self.input_bit)
+        self.RightShift = RightShift(QUANTIZE_BIT, self.rs_bit)
+        self.BiasAdd = BiasAdd()
+        self.Sp = Sp(QUANTIZE_BIT)
+        self.DeQuan = DeQuantity(self.output_bit)
+
+    def _quantize_params(self, layer, out_features):
+        """Shared body of NewConv2d.quantity / NewLinear.quantity (:135-163, :208-236)."""
+        self.weight = layer.weight
+        self.bias = layer.bias
+        assert self.weight is not None, "The weight can`t be None"
+        w = self.weight.data
+        if not w.is_cuda:
+            if not torch.cuda.is_available():
+                raise RuntimeError("no CUDA device: the integer simulation has no CPU fallback")
+            layer.cuda()
+            w = layer.weight.data
+        b = layer.bias.data if layer.bias is not None else torch.zeros(out_features, device=w.device)
+        wq = _quantize_param(w, self.weight_bit).view(w.shape)
+        bq = _quantize_param(b, self.bias_bit).view(b.shape)
+        # the wrapped layer keeps the integer-valued weights and a zero bias, like the reference
+        layer.weight = nn.Parameter(wq)
+        layer.bias = nn.Parameter(torch.zeros(out_features, device=w.device))
+        self.register_buffer("quantized_bias", bq)                      # fp32, integer-valued
+        self.register_buffer("_bias_i32", bq.to(torch.int32))
+        return wq
+
+
+class NewConv2d(_IntSimBase):
+    """Integer-simulated convolution (new_quantity_op.py:104-163)."""
+
+    def __init__(self, conv_module, quantize_infor):
+        super().__init__()
+        self._read_info(quantize_infor)
+        self.Conv = conv_module
+        self.quantity()
+
+    def quantity(self):
+        conv = self.Conv
+        if conv.groups != 1 or conv.dilation not in ((1, 1), 1) or conv.padding_mode != "zeros":
+            raise NotImplementedError("NewConv2d: groups=1, dilation=1, zero padding only")
+        wq = self._quantize_params(conv, conv.out_channels)
+        K, C, R, S = wq.shape
+        self._c_pad = _pad16(C)
+        w_krsc = torch.zeros((K, R, S, self._c_pad), dtype=torch.int8, device=wq.device)
+        w_krsc[..., :C] = wq.permute(0, 2, 3, 1).to(torch.int8)
+        self.register_buffer("_w_krsc", w_krsc.contiguous())
+
+    def forward(self, input):
+        conv = self.Conv
+        q = _native.quantize_nchw_to_nhwc_s8(input, self.input_bit, self._c_pad)        # Quan
+        out, _ = _native.conv2d_s8(q, self._w_krsc, self._bias_i32, conv.stride, conv.padding,
+                                   self.rs_bit, self.output_bit)  # Conv+RightShift+BiasAdd+Sp+DeQuan
+        return out
+
+
+class NewLinear(_IntSimBase):
+    """Integer-simulated fully connected layer (new_quantity_op.py:177-236)."""
+
+    def __init__(self, linear_module, quantize_infor):
+        super().__init__()
+        self._read_info(quantize_infor)
+        self.Linear = linear_module
+        self.quantity()
+
+    def quantity(self):
+        lin = self.Linear
+        wq = self._quantize_params(lin, lin.out_features)
+        N, K = wq.shape
+        self._k_pad = _pad16(K)
+        w = torch.zeros((N, self._k_pad), dtype=torch.int8, device=wq.device)
+        w[:, :K] = wq.to(torch.int8)
+        self.register_buffer("_w_nk", w.contiguous())
+
+    def forward(self, input):
+        x2 = input.reshape(-1, input.shape[-1])
+        # Quan: a [B][K] matrix is NCHW with H = W = 1, so the same kernel quantises and pads it
+        q = _native.quantize_nchw_to_nhwc_s8(x2.view(x2.shape[0], x2.shape[1], 1, 1), self.input_bit,
+                                             self._k_pad).view(x2.shape[0], self._k_pad)
+        out, _ = _native.gemm_s8(q, self._w_nk, self._bias_i32, self.rs_bit, self.output_bit)
+        return out.view(*input.shape[:-1], out.shape[-1])
+
+
+class NewAdd(nn.Module):
+    """clamp(x + y, -128, 127) on the de-quantised values (new_quantity_op.py:166-174)."""
+
+    def __init__(self):
+        super().__init__()
+        self.Sp = Sp(QUANTIZE_BIT)
+
+    def forward(self, x, y):
+        lo, hi = _range(QUANTIZE_BIT)
+        return _native.add_clamp(x, y, lo, hi).view(torch.broadcast_shapes(x.shape, y.shape))
+
+
+class QuanDequan(nn.Module):
+    """Power-of-two fake quantisation: clamp(round(x * 2^bit)) / 2^bit in one fused kernel
+    (new_quantity_op.py:239-257)."""
+
+    def __init__(self, Bitwidth, bit):
+        super().__init__()
+        self.bitwidth = Bitwidth
+        self.bit = bit
+
+    def forward(self, quantized_x):
+        lo, hi = (-128.0, 127.0) if self.bitwidth == 8 else (-32768.0, 32767.0)
+        return _native.fakequant(quantized_x, self.bit, lo, hi, dequant=True).view(quantized_x.shape)
+
+
+def _dump_diagnostics(path, name, tag, before, after):
+    """Text dump of a parameter before / after fake-quant (new_quantity_op.py:312-326); the
+    PNG histograms (:328-337) are drawn only if matplotlib is importable."""
+    stem = os.path.join(path, name.replace(".", "_") + "_" + tag)
+    with open(stem + ".txt", "a") as f:
+        for t in (before, after):
+            f.write("  ".join(str(v) for v in t.detach().cpu().numpy().flatten()) + "\n\n\n\n")
+    try:
+        import matplotlib.pyplot as plt
+    except ImportError:
+        return
+    for suffix, t in (("_o.png", before), ("_q.png", after)):
+        fig = plt.figure()
+        plt.grid()
+        plt.title(tag)
+        plt.xlabel("bins")
+        plt.ylabel("counter/frequency")
+        plt.hist(t.detach().cpu().numpy().flatten(), 2048, density=True, histtype="bar", facecolor="blue")
+        fig.savefig(stem + suffix, bbox_inches="tight")
+        plt.close(fig)
+
+
+class _FakeQuantBase(nn.Module):
+    def _setup(self, name, module, quantize_infor, new_model_path, out_features):
+        self.name = name
+        self.path = os.path.join(os.path.dirname(new_model_path), "quantity_results")
+        if WRITE_DIAGNOSTICS and not os.path.exists(self.path):
+            os.makedirs(self.path)
+        self.weight_bit = quantize_infor["weight_bit"]
+        self.bias_bit = quantize_infor["bias_bit"]
+        self.input_bit = quantize_infor["input_bit"]
+        self.output_bit = quantize_infor["output_bit"]
+        self.weight_qdp = QuanDequan(QUANTIZE_BIT, self.weight_bit)
+        self.bias_qdp = QuanDequan(QUANTIZE_BIT, self.bias_bit)
+        self.output_qdp = QuanDequan(QUANTIZE_BIT, self.output_bit)
+        self._out_features = out_features
+
+    def _feature_extract(self, layer):
+        """Fake-quantise weight and bias once and write them back (:294-309, :392-407)."""
+        self.weight = layer.weight
+        self.bias = layer.bias
+        assert self.weight is not None, "The layer weight can`t be None"
+        if not layer.weight.is_cuda:
+            if not torch.cuda.is_available():
+                raise RuntimeError("no CUDA device: the fake-quant simulation has no CPU fallback")
+            layer.cuda()
+        w = layer.weight.data
+        b = layer.bias.data if layer.bias is not None else torch.zeros(self._out_features, device=w.device)
+        w_qdp = self.weight_qdp(w)
+        b_qdp = self.bias_qdp(b)
+        layer.weight = nn.Parameter(w_qdp)
+        layer.bias = nn.Parameter(b_qdp)
+        if WRITE_DIAGNOSTICS:
+            _dump_diagnostics(self.path, self.name, "weight", w, w_qdp)
+            _dump_diagnostics(self.path, self.name, "bias", b, b_qdp)
+
+
+class TestConv(_FakeQuantBase):
+    """Fake-quant convolution (new_quantity_op.py:259-355)."""
+    __test__ = False      # not a pytest class
+
+    def __init__(self, name, module, quantize_infor, new_model_path):
+        super().__init__()
+        self._setup(name, module, quantize_infor, new_model_path, module.out_channels)
+        self.Conv = module
+        self.feature_extract()
+
+    def feature_extract(self):
+        self._feature_extract(self.Conv)
+
+    def forward(self, x):
+        return self.output_qdp(self.Conv(x))
+
+
+class TestLinear(_FakeQuantBase):
+    """Fake-quant fully connected layer (new_quantity_op.py:358-452)."""
+    __test__ = False
+
+    def __init__(self, name, module, quantize_infor, new_model_path):
+        super().__init__()
+        self._setup(name, module, quantize_infor, new_model_path, module.out_features)
+        self.linear = module
+        self.feature_extract()
+
+    def feature_extract(self):
+        self._feature_extract(self.linear)
+
+    def forward(self, x):
+        return self.output_qdp(self.linear(x))

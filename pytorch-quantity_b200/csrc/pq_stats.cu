@@ -1,0 +1,71 @@
+// pq_stats.cu -- C-ABI entry points for the statistics kernels.
+#include "pq_stats_kernels.cuh"
+
+namespace {
+
+constexpr int kHistCopies = 1;   // privatised sub-histograms per CTA (histogram)
+
+int build_table(pq::SegTable &t, const float *const *xs, const uint64_t *ns, const float *params, int k)
+{
+    if (k < 0 || (k > 0 && (!xs || !ns))) return PQ_EINVAL;
+    if (k > PQ_MAX_SEGMENTS) return PQ_ETOOMANY;
+    unsigned long long total = 0;
+    for (int i = 0; i < k; ++i) {
+        if (ns[i] && !xs[i]) return PQ_EINVAL;
+        if (((unsigned long long)xs[i] & 3ull) != 0) return PQ_EALIGN;
+        t.ptr[i] = xs[i];
+        t.n[i] = ns[i];
+        t.param[i] = params ? params[i] : 0.0f;
+        total += pq::seg_num_chunks(xs[i], ns[i]);
+        if (total > 0xffffffffull) return PQ_EUNSUPPORTED;
+        t.chunk_end[i] = (unsigned int)total;
+    }
+    t.k = k;
+    t.total_chunks = (unsigned int)total;
+    return PQ_OK;
+}
+
+unsigned int grid_for(unsigned int total_chunks, int ctas_per_sm)
+{
+    unsigned int g = (unsigned int)(pq::kNumSMs * ctas_per_sm);
+    return total_chunks < g ? total_chunks : g;
+}
+
+}  // namespace
+
+extern "C" int pq_absmax_multi_f32(const float *const *xs_host, const uint64_t *ns_host, int k,
+                                   uint32_t *max_bits, pq_stream_t stream)
+{
+    if (k == 0) return PQ_OK;
+    if (!max_bits) return PQ_EINVAL;
+    pq::SegTable t;
+    int rc = build_table(t, xs_host, ns_host, nullptr, k);
+    if (rc != PQ_OK) return rc;
+    pq::absmax_multi_kernel<<<grid_for(t.total_chunks, 8), pq::kStatThreads, 0, (cudaStream_t)stream>>>(
+        t, max_bits);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pq_hist2048_multi_f32(const float *const *xs_host, const uint64_t *ns_host,
+                                     const float *intervals_host, int k, long long *hist,
+                                     pq_stream_t stream)
+{
+    if (k == 0) return PQ_OK;
+    if (!hist || !intervals_host) return PQ_EINVAL;
+    for (int i = 0; i < k; ++i)
+        if (!(intervals_host[i] > 0.0f)) return PQ_EINVAL;   // also rejects NaN
+    pq::SegTable t;
+    int rc = build_table(t, xs_host, ns_host, intervals_host, k);
+    if (rc != PQ_OK) return rc;
+    constexpr size_t smem = pq::hist_smem_bytes(kHistCopies);
+    auto kern = pq::hist_multi_kernel<kHistCopies>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int ctas_per_sm = (int)((200 * 1024) / smem) < 8 ? (int)((200 * 1024) / smem) : 8;
+    kern<<<grid_for(t.total_chunks, ctas_per_sm), pq::kStatThreads, smem, (cudaStream_t)stream>>>(
+        t, reinterpret_cast<unsigned long long *>(hist));
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,289 @@
+// pq_stats_kernels.cuh -- activation / weight statistics kernels (subsystem 1):
+//   absmax_multi_kernel : per-tensor max |x|           (distribution_collector.py:70-78)
+//   hist_multi_kernel   : 2048-bin |x| histograms      (distribution_collector.py:127-135)
+//
+// Both are HBM-bound streaming kernels: 4 algorithmic bytes per element per pass.
+// One launch covers up to PQ_MAX_SEGMENTS tensors.  Every tensor is cut into chunks of
+// kChunkElems elements; each CTA owns a CONTIGUOUS range of chunks, so it touches the
+// fewest possible tensors and publishes its private result once per tensor it touched.
+#pragma once
+#include "pq_common.cuh"
+
+namespace pq {
+
+constexpr int kStatThreads = 256;
+constexpr int kVecPerThread = 8;                                 // float4 loads in flight per thread
+constexpr int kChunkVecs = kStatThreads * kVecPerThread;         // 2048 float4
+constexpr int kChunkElems = kChunkVecs * 4;                      // 8192 elements = 32 KB
+
+// Geometry of one segment: scalar head up to the first 16-byte boundary, float4 body, scalar tail.
+struct SegGeom {
+    const float *p;
+    unsigned long long n;
+    unsigned int head;              // scalar elements before the aligned body
+    unsigned long long nvec;        // float4 count of the body
+    const float4 *body;
+    unsigned int tail;              // scalar elements after the body
+};
+
+__device__ __forceinline__ SegGeom seg_geom(const SegTable &t, int s)
+{
+    SegGeom g;
+    g.p = t.ptr[s];
+    g.n = t.n[s];
+    unsigned long long addr = (unsigned long long)g.p;
+    unsigned long long head = ((16ull - (addr & 15ull)) & 15ull) >> 2;
+    g.head = (unsigned int)(head < g.n ? head : g.n);
+    g.nvec = (g.n - g.head) >> 2;
+    g.body = reinterpret_cast<const float4 *>(g.p + g.head);
+    g.tail = (unsigned int)(g.n - g.head - (g.nvec << 2));
+    return g;
+}
+
+__host__ __device__ inline unsigned int seg_num_chunks(const float *p, unsigned long long n)
+{
+    unsigned long long addr = (unsigned long long)p;
+    unsigned long long head = ((16ull - (addr & 15ull)) & 15ull) >> 2;
+    if (head > n) head = n;
+    unsigned long long nvec = (n - head) >> 2;
+    unsigned long long c = (nvec + kChunkVecs - 1) / kChunkVecs;
+    return (unsigned int)(c ? c : 1);
+}
+
+// ------------------------------------------------------------------------------ absmax
+__device__ __forceinline__ unsigned int absbits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+
+__global__ void __launch_bounds__(kStatThreads)
+absmax_multi_kernel(const __grid_constant__ SegTable tab, unsigned int *__restrict__ max_bits)
+{
+    __shared__ unsigned int s_warp[kStatThreads / 32];
+    const unsigned int per = (tab.total_chunks + gridDim.x - 1) / gridDim.x;
+    unsigned int c = blockIdx.x * per;
+    const unsigned int c_end = min(c + per, tab.total_chunks);
+    if (c >= c_end) return;
+
+    int seg = seg_of_chunk(tab, c);
+    unsigned int m = 0;
+    while (c < c_end) {
+        const SegGeom g = seg_geom(tab, seg);
+        const unsigned int seg_first = seg ? tab.chunk_end[seg - 1] : 0;
+        const unsigned int seg_last = min(tab.chunk_end[seg], c_end);
+        for (; c < seg_last; ++c) {
+            const unsigned long long v0 = (unsigned long long)(c - seg_first) * kChunkVecs;
+            const float4 *src = g.body + v0;
+            const unsigned long long left = g.nvec > v0 ? g.nvec - v0 : 0;
+            if (left >= (unsigned long long)kChunkVecs) {
+                float4 v[kVecPerThread];
+#pragma unroll
+                for (int i = 0; i < kVecPerThread; ++i) v[i] = ld_stream_f4(src + threadIdx.x + i * kStatThreads);
+#pragma unroll
+                for (int i = 0; i < kVecPerThread; ++i)
+                    m = max(max(m, max(absbits(v[i].x), absbits(v[i].y))), max(absbits(v[i].z), absbits(v[i].w)));
+            } else {
+                for (unsigned int i = threadIdx.x; i < (unsigned int)left; i += kStatThreads) {
+                    float4 v = ld_stream_f4(src + i);
+                    m = max(max(m, max(absbits(v.x), absbits(v.y))), max(absbits(v.z), absbits(v.w)));
+                }
+            }
+            if (c == seg_first) {   // the segment's first chunk also owns the unaligned head / tail
+                if (threadIdx.x < g.head) m = max(m, absbits(g.p[threadIdx.x]));
+                if (threadIdx.x < g.tail) m = max(m, absbits(g.p[g.n - g.tail + threadIdx.x]));
+            }
+        }
+        // publish this CTA's maximum for the segment: warp redux, one atomic per CTA
+        m = __reduce_max_sync(0xffffffffu, m);
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned int w = threadIdx.x < kStatThreads / 32 ? s_warp[threadIdx.x] : 0u;
+            w = __reduce_max_sync(0xffffffffu, w);
+            if (threadIdx.x == 0 && w != 0) atomicMax(max_bits + seg, w);
+        }
+        __syncthreads();
+        m = 0;
+        ++seg;
+    }
+}
+
+// --------------------------------------------------------------------------- histogram
+// Bin index of the reference: idx = min((int)trunc(fl32(|x| / interval)), 2047) for x != 0, where
+// the division is IEEE round-to-nearest.  A literal __fdiv_rn costs MUFU.RCP + FCHK + 5 FFMA + a
+// slow-path call per element and caps the kernel at ~63 % of HBM bandwidth (profiles/).  The fast
+// path below is exact by construction:
+//   q0 = a * r,  e = fma(-q0, d, a),  q1 = fma(e, r, q0)     with r = RN(1/d) hoisted per tensor
+// gives |q1 - RN(a/d)| <= a few ulps (<< 2^-10 for q1 < 2048).  u = RZ(min(q1, 2047.5) + 2048) then
+// holds trunc(q1) in mantissa bits [12,23) and the first 12 fraction bits f below them.  If
+// 4 <= f < 4092, q1 is at least 2^-10 away from every integer, so trunc(RN(a/d)) == trunc(q1).
+// Otherwise (0.2 % of elements, plus every zero) the element is handed to the exact slow path,
+// which performs the real division.  (NaN inputs are undefined in the reference; here they count
+// in the top bin.)
+struct HistDiv {
+    float d;        // bin width
+    float r;        // RN(1/d)
+};
+
+__device__ __forceinline__ HistDiv make_hist_div(float interval)
+{
+    HistDiv h;
+    h.d = interval;
+    h.r = __frcp_rn(interval);
+    return h;
+}
+
+// exact (reference-literal) path for one element
+__device__ __forceinline__ void hist_add_exact(unsigned int *sh, float v, float interval)
+{
+    if (v != 0.0f) {                                       // bins are (lo, hi]: zeros are skipped
+        const float q = __fdiv_rn(fabsf(v), interval);     // IEEE division, as numpy float32 / float32
+        const int idx = q >= 2047.0f ? 2047 : (int)q;      // trunc + clamp (np.minimum(..., 2047))
+        atomicAdd(sh + idx, 1u);
+    }
+}
+
+// Shared-memory layout per CTA: COPIES histograms of 2048 words, each 8 KB-aligned in the shared
+// window so that `(bits >> 10) & 0x1ffc | base` is ONE logic op, followed by one trash word per
+// CTA that absorbs the (unconditional) atomics of elements routed to the slow path.
+constexpr unsigned int kSlowThreshold = 0xff800000u;
+
+__device__ __forceinline__ unsigned int hist_fast_bits(float v, const HistDiv &h)
+{
+    const float a = fabsf(v);
+    const float q0 = __fmul_rn(a, h.r);
+    const float e = fmaf(-q0, h.d, a);
+    // clamp at 2047.5: anything at or beyond lands in the top bin on the fast path (its true
+    // quotient is > 2047), while [2047, 2047.5) still gets the near-integer check at 2047.0
+    const float q1 = fminf(fmaf(e, h.r, q0), 2047.5f);
+    return __float_as_uint(__fadd_rz(q1, 2048.0f));
+}
+
+// f = bits & 0xfff must lie in [4, 4092): shift it to the top of the word and range-check
+__device__ __forceinline__ bool hist_is_slow(unsigned int bits)
+{
+    return (bits * 0x100000u - 0x400000u) >= kSlowThreshold;
+}
+
+// fast path for one element: always exactly one shared atomic (no divergent region).  Returns
+// whether the element must be re-done exactly.  An exact zero always looks "slow" (q = 0 sits on an
+// integer) and is routed to the trash word; ZERO_AWARE additionally keeps it from raising the
+// redo flag (+2 instructions), which matters only for sparse tensors (post-ReLU, zero padding).
+template <bool ZERO_AWARE>
+__device__ __forceinline__ bool hist_add_fast(unsigned int base_addr, unsigned int trash_addr, float v,
+                                              const HistDiv &h)
+{
+    const unsigned int bits = hist_fast_bits(v, h);
+    const bool slow = hist_is_slow(bits);
+    const unsigned int addr = slow ? trash_addr : (((bits >> 10) & 0x1ffcu) | base_addr);
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+    return ZERO_AWARE ? (slow && v != 0.0f) : slow;
+}
+
+// one thread's share of a full chunk part: VPT float4 -> bit i of the result flags float4 i
+template <bool ZERO_AWARE, int VPT>
+__device__ __forceinline__ unsigned int hist_add_vecs(unsigned int base_addr, unsigned int trash_addr,
+                                                      const float4 (&v)[VPT], const HistDiv &h)
+{
+    unsigned int redo = 0;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const bool s0 = hist_add_fast<ZERO_AWARE>(base_addr, trash_addr, v[i].x, h);
+        const bool s1 = hist_add_fast<ZERO_AWARE>(base_addr, trash_addr, v[i].y, h);
+        const bool s2 = hist_add_fast<ZERO_AWARE>(base_addr, trash_addr, v[i].z, h);
+        const bool s3 = hist_add_fast<ZERO_AWARE>(base_addr, trash_addr, v[i].w, h);
+        if (s0 | s1 | s2 | s3) redo |= 1u << i;
+    }
+    return redo;
+}
+
+constexpr size_t hist_smem_bytes(int copies) { return 8192 + (size_t)copies * PQ_HIST_BINS * 4 + 128; }
+
+template <int COPIES, int VPT = kVecPerThread>
+__global__ void __launch_bounds__(kStatThreads, VPT <= 4 ? 6 : 4)
+hist_multi_kernel(const __grid_constant__ SegTable tab, unsigned long long *__restrict__ hist)
+{
+    // dynamic shared memory: hist_smem_bytes(COPIES)
+    extern __shared__ unsigned int s_raw[];                // 8 KB alignment slack + [COPIES][2048] + trash
+    // align the histograms to 8 KB inside the shared window (see hist_add_fast)
+    const unsigned int raw_addr = (unsigned int)__cvta_generic_to_shared(s_raw);
+    const unsigned int pad = ((8192u - (raw_addr & 8191u)) & 8191u) >> 2;
+    unsigned int *s_hist = s_raw + pad;
+    const unsigned int per = (tab.total_chunks + gridDim.x - 1) / gridDim.x;
+    unsigned int c = blockIdx.x * per;
+    const unsigned int c_end = min(c + per, tab.total_chunks);
+    if (c >= c_end) return;
+
+    for (int i = threadIdx.x; i < COPIES * PQ_HIST_BINS; i += kStatThreads) s_hist[i] = 0;
+    __syncthreads();
+    unsigned int *mine = s_hist + ((threadIdx.x >> 5) % COPIES) * PQ_HIST_BINS;
+    const unsigned int mine_addr = (unsigned int)__cvta_generic_to_shared(mine);
+    const unsigned int trash_addr = (unsigned int)__cvta_generic_to_shared(s_hist + COPIES * PQ_HIST_BINS);
+
+    int seg = seg_of_chunk(tab, c);
+    bool zero_aware = false;                               // warp-uniform
+    while (c < c_end) {
+        const SegGeom g = seg_geom(tab, seg);
+        const float interval = tab.param[seg];
+        const HistDiv hd = make_hist_div(interval);
+        const unsigned int seg_first = seg ? tab.chunk_end[seg - 1] : 0;
+        const unsigned int seg_last = min(tab.chunk_end[seg], c_end);
+        for (; c < seg_last; ++c) {
+            const unsigned long long v0 = (unsigned long long)(c - seg_first) * kChunkVecs;
+            const float4 *src = g.body + v0;
+            const unsigned long long left = g.nvec > v0 ? g.nvec - v0 : 0;
+            if (left >= (unsigned long long)kChunkVecs) {
+#pragma unroll 1
+                for (int part = 0; part < kVecPerThread / VPT; ++part) {
+                    const float4 *psrc = src + part * VPT * kStatThreads;
+                    float4 v[VPT];
+#pragma unroll
+                    for (int i = 0; i < VPT; ++i) v[i] = ld_stream_f4(psrc + threadIdx.x + i * kStatThreads);
+                    unsigned int redo;                      // bit i: float4 i holds a slow element
+                    if (zero_aware) {
+                        redo = hist_add_vecs<true, VPT>(mine_addr, trash_addr, v, hd);
+                    } else {
+                        redo = hist_add_vecs<false, VPT>(mine_addr, trash_addr, v, hd);
+                        // a warp that keeps flagging (exact zeros in the data) switches, for the rest
+                        // of its chunk range, to the variant that does not flag zeros
+                        zero_aware = __any_sync(0xffffffffu, __popc(redo) >= 3);
+                    }
+                    while (redo) {                          // rare: re-load the flagged float4s
+                        const int slot = __ffs(redo) - 1;
+                        redo &= redo - 1;
+                        const float4 w = psrc[threadIdx.x + slot * kStatThreads];
+                        if (hist_is_slow(hist_fast_bits(w.x, hd))) hist_add_exact(mine, w.x, interval);
+                        if (hist_is_slow(hist_fast_bits(w.y, hd))) hist_add_exact(mine, w.y, interval);
+                        if (hist_is_slow(hist_fast_bits(w.z, hd))) hist_add_exact(mine, w.z, interval);
+                        if (hist_is_slow(hist_fast_bits(w.w, hd))) hist_add_exact(mine, w.w, interval);
+                    }
+                }
+            } else {
+                for (unsigned int i = threadIdx.x; i < (unsigned int)left; i += kStatThreads) {
+                    const float4 v = ld_stream_f4(src + i);
+                    hist_add_exact(mine, v.x, interval);
+                    hist_add_exact(mine, v.y, interval);
+                    hist_add_exact(mine, v.z, interval);
+                    hist_add_exact(mine, v.w, interval);
+                }
+            }
+            if (c == seg_first) {
+                if (threadIdx.x < g.head) hist_add_exact(mine, g.p[threadIdx.x], interval);
+                if (threadIdx.x < g.tail) hist_add_exact(mine, g.p[g.n - g.tail + threadIdx.x], interval);
+            }
+        }
+        // publish: fold the copies, add the non-empty bins to the tensor's global histogram
+        __syncthreads();
+        unsigned long long *out = hist + (size_t)seg * PQ_HIST_BINS;
+        for (int b = threadIdx.x; b < PQ_HIST_BINS; b += kStatThreads) {
+            unsigned int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < COPIES; ++k) {
+                cnt += s_hist[k * PQ_HIST_BINS + b];
+                s_hist[k * PQ_HIST_BINS + b] = 0;
+            }
+            if (cnt) atomicAdd(out + b, (unsigned long long)cnt);
+        }
+        __syncthreads();
+        ++seg;
+    }
+}
+
+}  // namespace pq

@@ -1,0 +1,161 @@
+"""End-to-end parity of the drop-in drivers on the GPU against the golden run of the
+unmodified reference drivers (tests/golden/tiny_e2e.npz, r18_224_c1.npz)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_json, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _configs(tmp_path, input_shape, max_cali):
+    import tools._config as tc
+    cfg = tc.load_tool_config(os.path.join(os.path.dirname(tc.__file__), "configs.yml"))
+    wd = str(tmp_path / "workdir")
+    cfg["OUTPUT"] = {"WORK_DIR": wd, "WEIGHT_BIT_TABLE": wd + "/weight.table",
+                     "FEAT_BIT_TABLE": wd + "/feat.table", "WEIGHT_DIR": wd + "/weight",
+                     "BIAS_DIR": wd + "/bias", "FINAL_WEIGHT_DIR": wd + "/new_weight",
+                     "FINAL_BIAS_DIR": wd + "/new_bias"}
+    cfg["SETTINGS"]["MAX_CALI_IMG_NUM"] = max_cali
+    user = tc.load_user_config({"PATH": {}, "MODEL": {"INPUT_SHAPE": ",".join(map(str, input_shape))},
+                                "PRE_PROCESS": {"IMG": 1}, "SETTINGS": {"DEVICE": "gpu", "GPU": 0}})
+    return cfg, user
+
+
+def _tiny_model(g):
+    import tiny_fabu_net as tn
+    net = tn.build_tiny(0)
+    sd = {k[len("state/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
+    net.load_state_dict(sd)
+    return net.eval()
+
+
+def _snapshot(cfg):
+    out = cfg["OUTPUT"]
+    snap = {"feat.table": open(out["FEAT_BIT_TABLE"]).read(), "weight.table": open(out["WEIGHT_BIT_TABLE"]).read()}
+    for key, sub in (("WEIGHT_DIR", "weight"), ("BIAS_DIR", "bias"), ("FINAL_WEIGHT_DIR", "new_weight"),
+                     ("FINAL_BIAS_DIR", "new_bias")):
+        for fn in sorted(os.listdir(out[key])):
+            snap[sub + "/" + fn] = open(os.path.join(out[key], fn), "rb").read()
+    return snap
+
+
+def test_tiny_calibration_and_tables(tmp_path):
+    """Tracer names, merge groups, per-tensor statistics on the golden activations, feat.table,
+    weight.table, weight / bias JSON (md5) after weight_quantize and after the script's second
+    rewrite_weight (quirk Q7)."""
+    import hashlib
+    import common.quantity as cq
+    import tools
+    g = load_golden("tiny_e2e.npz")
+    j = golden_json(g)
+    cfg, user = _configs(tmp_path, (1, 3, 16, 16), 2)
+    with torch.no_grad():
+        net = cq.merge_bn(_tiny_model(g), "cpu")
+        q = tools.Quantity(net, config=cfg, user_config=user, verbose=False)
+        assert {k: v for k, v in q.net_info.items()} == j["net_info"]
+        assert list(q.net_info) == list(j["net_info"])
+        assert q.cared_op_layer_names == j["cared_op_layer_names"]
+        assert q.get_merge_groups(q.net_info) == j["merge_groups"]
+        batches = [(torch.from_numpy(g["batch%d" % i]), None) for i in range(3)]
+        q.activation_quantize(batches)
+        # the GPU forward (cuDNN) is not bitwise the CPU forward (MKLDNN) of the golden run, so
+        # bit-exact statistics parity is pinned at the statistics boundary in the next test; the
+        # table (coarse fractional bits) must still agree:
+        assert open(cfg["OUTPUT"]["FEAT_BIT_TABLE"]).read() == j["after_weight_quantize"]["feat.table"]
+        q.weight_quantize()
+        snap1 = _snapshot(cfg)
+        q.rewrite_weight()
+        snap2 = _snapshot(cfg)
+    for snap, key in ((snap1, "after_weight_quantize"), (snap2, "after_second_rewrite")):
+        ref = j[key]
+        assert snap["weight.table"] == ref["weight.table"]
+        for name, val in ref.items():
+            if isinstance(val, dict):
+                assert hashlib.md5(snap[name]).hexdigest() == val["md5"], (key, name)
+
+
+def test_tiny_statistics_boundary_bit_exact():
+    """Identical activation tensors in (the reference run's hooked tensors) -> identical maxima,
+    intervals, histograms (incl. merged groups), thresholds and bits out."""
+    import common.quantity as cq
+    g = load_golden("tiny_e2e.npz")
+    j = golden_json(g)
+    net_info, groups = j["net_info"], j["merge_groups"]
+    top = ["image"] + list(net_info)
+    col = cq.DistributionCollector(top, worker_num=2)
+    feats = []
+    i = 0
+    while "feat%d/image" % i in g.files:
+        feats.append({n: torch.from_numpy(g["feat%d/%s" % (i, n)]).cuda() for n in top})
+        i += 1
+    for f in feats:
+        col.refresh_max_val(f)
+    intervals = col.distribution_intervals
+
+    def has_elt(names):
+        return any(net_info[n]["type"] == "Eltwise" for n in names)
+
+    for names in groups:
+        if not has_elt(names):
+            w = max(intervals[n] for n in names)
+            for n in names:
+                intervals[n] = w
+    for n in top:
+        assert float(intervals[n]) == j["intervals"][n], n
+    for f in feats:
+        col.add_to_distributions(f)
+    dists = col.distributions
+    for names in groups:
+        if not has_elt(names):
+            tot = np.zeros(2048)
+            for n in names:
+                tot += dists[n]
+            for n in names:
+                dists[n] = tot
+    for n in top:
+        assert np.array_equal(np.asarray(dists[n], dtype=np.float64), g["dist/" + n].astype(np.float64)), n
+    qz = cq.Quantizer(top)
+    qz.quantize(dists, intervals)
+    assert qz.bits == j["raw_bits"]
+    for n in top:
+        assert float(qz.threshold_value[n]) == j["thresholds"][n], n
+
+
+def test_tiny_recontest_outputs(tmp_path):
+    """ReconTest (fake-quant) model: per-layer outputs vs the reference's, on the GPU.  The conv
+    itself is cuDNN vs MKLDNN fp32, so outputs may differ by one quantisation step where the
+    pre-rounding value sits on a tie; the fake-quant grid and range must hold exactly."""
+    import common.quantity as cq
+    import tools
+    g = load_golden("tiny_e2e.npz")
+    j = golden_json(g)
+    cfg, user = _configs(tmp_path, (1, 3, 16, 16), 2)
+    os.makedirs(cfg["OUTPUT"]["WORK_DIR"], exist_ok=True)
+    open(cfg["OUTPUT"]["FEAT_BIT_TABLE"], "w").write(j["after_second_rewrite"]["feat.table"])
+    open(cfg["OUTPUT"]["WEIGHT_BIT_TABLE"], "w").write(j["after_second_rewrite"]["weight.table"])
+    with torch.no_grad():
+        net = _tiny_model(g)
+        r = tools.Reconstruction(net, config=cfg)
+        r.merge_bn()
+        info = r.get_quantity_information()
+        ref_info = j["quantity_information"]
+        for name, d in ref_info.items():
+            for key in ("weight_bit", "bias_bit", "output_bit", "input_bit"):
+                assert info[name][key] == d[key], (name, key)
+        model = r.ReconTest(info, str(tmp_path / "workdir" / "ReconTest.pth")).cuda()
+        outs = {}
+        for name, mod in model.named_modules():
+            if type(mod).__name__ in ("TestConv", "TestLinear", "NewAdd"):
+                mod.register_forward_hook(lambda m, i, o, name=name: outs.__setitem__(name, o.cpu().numpy()))
+        y = model(torch.from_numpy(g["eval_batch"]).cuda()).cpu().numpy()
+    # first layer sees identical inputs; its fake-quantised weights are bit-exact
+    ref0 = g["ReconTest/layer/conv0.0"]
+    step = 2.0 ** -info["conv0.0"]["output_bit"]
+    assert np.abs(outs["conv0.0"] - ref0).max() <= step
+    assert (outs["conv0.0"] != ref0).mean() < 1e-3
+    assert np.abs(y - g["ReconTest/y"]).max() <= 4 * 2.0 ** -info["fc"]["output_bit"]

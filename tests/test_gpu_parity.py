@@ -1,0 +1,284 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI by the drop-in Python classes,
+against (1) the golden vectors of the unmodified reference and (2) the CPU oracle on the same
+seeded inputs.  Bit-exact for counts, maxima, thresholds, bits, fake-quant and integer
+simulation; KL divergences within 1e-9 relative (north_star allows 1e-5)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import det_inputs
+from conftest import golden_json, load_golden
+from golden import gen_golden as gg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cq():
+    import common.quantity as cq
+    from common.quantity import _native
+    _native.lib()                       # fail loudly if the CUDA library is missing
+    return cq
+
+
+def _meta(npz):
+    return json.loads(bytes(npz["meta"]).decode())
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+# ------------------------------------------------------------------ a1 / a2 / a3
+@pytest.mark.parametrize("case", list(det_inputs.stats_cases()))
+@pytest.mark.parametrize("as_numpy", [False, True])
+def test_stats_case_vs_golden(cq, oracle, case, as_numpy):
+    g = load_golden("stats.npz")
+    batches = det_inputs.stats_cases()[case]
+    col = cq.DistributionCollector([case], worker_num=4)
+    for b in batches:
+        col.refresh_max_val({case: b if as_numpy else dev(b)})
+    m = col.max_vals[case]
+    assert float(m) == float(g[case + "/max"][0])
+    assert type(m).__name__ == _meta(g)[case]["max_type"]
+    iv = col.distribution_intervals[case]
+    assert float(iv) == float(g[case + "/interval"][0])
+    assert type(iv).__name__ == _meta(g)[case]["interval_type"]
+    for b in batches:
+        col.add_to_distributions({case: b if as_numpy else dev(b)})
+    h = col.distributions[case]
+    assert h.dtype == np.int32
+    assert np.array_equal(h, g[case + "/hist"])
+
+
+def test_stats_multi_tensor_one_launch(cq, oracle):
+    """All cases in ONE collector (one multi-tensor launch per pass) == per-case results."""
+    g = load_golden("stats.npz")
+    cases = det_inputs.stats_cases()
+    names = list(cases)
+    col = cq.DistributionCollector(names)
+    first = {n: dev(cases[n][0]) for n in names}
+    col.refresh_max_val(first)
+    col.add_to_distributions(first)
+    for n in names:
+        assert float(col.distribution_intervals[n]) == float(g["pool3/" + n + "/interval"][0])
+        assert np.array_equal(col.distributions[n], g["pool3/" + n + "/hist"]), n
+
+
+@pytest.mark.parametrize("offset", [1, 2, 3, 5])
+def test_stats_unaligned_views(cq, oracle, offset):
+    """Views that start off a 16-byte boundary take the scalar head/tail path."""
+    base = det_inputs.bell(100003, 77)
+    x = base[offset:offset + 99991]
+    t = dev(base)[offset:offset + 99991]
+    col = cq.DistributionCollector(["x"])
+    col.refresh_max_val({"x": t})
+    m = oracle.absmax_update(0, x)
+    assert float(col.max_vals["x"]) == float(m)
+    col.add_to_distributions({"x": t})
+    assert np.array_equal(col.distributions["x"], oracle.hist(x, oracle.interval(m)))
+
+
+@pytest.mark.parametrize("kind", ["bell", "relu", "const", "tail"])
+def test_stats_large_vs_oracle(cq, oracle, kind):
+    n = 6_000_011
+    x = {"bell": lambda: det_inputs.bell(n, 5),
+         "relu": lambda: det_inputs.relu_bell(n, 6),
+         "const": lambda: det_inputs.constant(n, -2.5),
+         "tail": lambda: det_inputs.heavy_tail(n, 7)}[kind]()
+    col = cq.DistributionCollector(["x"])
+    col.refresh_max_val({"x": dev(x)})
+    m = oracle.absmax_update(0, x)
+    assert float(col.max_vals["x"]) == float(m)
+    col.add_to_distributions({"x": dev(x)})
+    assert np.array_equal(col.distributions["x"], oracle.hist(x, oracle.interval(m)))
+
+
+def test_hist_division_exactness_at_bin_edges(cq, oracle):
+    """The kernel replaces the IEEE division by reciprocal-multiply + FMA correction with an exact
+    fallback; stress it where it could go wrong: values within +-3 ulps of EVERY bin edge k*d, for
+    divisors that are powers of two, have all-ones / sparse mantissas, are tiny or huge."""
+    rng = np.random.default_rng(11)
+    ds = [np.float32(v) for v in (2.0 ** -9, 2.0 ** -20, 1.0, 3.0, 1e-12, 1.1754944e-38 * 4096, 1.6e35,
+                                  0.0013031913, 7.0, 4.8828125, 1.9999999, 1.0000001, 0.33333334)]
+    ds += [np.uint32(0x3a7fffff).view(np.float32), np.uint32(0x3affffff).view(np.float32),
+           np.uint32(0x3a800001).view(np.float32)]
+    ds += [np.float32(v) for v in np.exp(rng.uniform(np.log(1e-8), np.log(1e3), size=24))]
+    names, tensors, expect = [], {}, {}
+    for i, d in enumerate(ds):
+        k = np.arange(1, 2050, dtype=np.float64)
+        base = (k * np.float64(d)).astype(np.float32)
+        vals = [base]
+        up, dn = base.copy(), base.copy()
+        for _ in range(3):
+            up = np.nextafter(up, np.float32(np.inf)); dn = np.nextafter(dn, np.float32(0))
+            vals += [up.copy(), dn.copy()]
+        x = np.concatenate(vals + [-(base), (rng.random(5000) * 2048 * float(d)).astype(np.float32)])
+        x = x[np.isfinite(x)]
+        n = "d%d" % i
+        names.append(n); tensors[n] = x; expect[n] = oracle.hist(x, d)
+    col = cq.DistributionCollector(names)
+    col.refresh_max_val({n: dev(tensors[n]) for n in names})
+    col.distribution_intervals                         # materialise, then override the bin widths
+    for n, d in zip(names, ds):
+        col._distribution_intervals[n] = d
+    col.add_to_distributions({n: dev(tensors[n]) for n in names})
+    for n in names:
+        assert np.array_equal(col.distributions[n], expect[n]), (n, float(col._distribution_intervals[n]))
+
+
+def test_stats_full_size_properties(cq):
+    """BASELINE-scale tensor (2^28 elements = 1 GiB): size-independent properties.
+    sum(hist) == #non-zeros; hist(a) + hist(b) == hist(a ++ b); max == torch's."""
+    n = 1 << 28
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(n, device="cuda", generator=g)
+    x[::7] = 0.0
+    col = cq.DistributionCollector(["x"])
+    col.refresh_max_val({"x": x})
+    assert float(col.max_vals["x"]) == float(x.abs().max())
+    col.add_to_distributions({"x": x})
+    whole = col._hist.clone()
+    assert int(whole.sum()) == int((x != 0).sum())
+    iv = col.distribution_intervals["x"]
+    # reference arithmetic on the device with torch ops as an independent cross-check
+    # (a 0-dim CUDA divisor forces a true IEEE division; a python scalar would become x * (1/iv))
+    idx = torch.clamp((x[x != 0].abs() / torch.tensor(float(iv), device="cuda")).to(torch.int32), max=2047)
+    assert torch.equal(torch.bincount(idx, minlength=2048), whole[0])
+    col2 = cq.DistributionCollector(["x"])
+    col2.refresh_max_val({"x": x})
+    half = n // 2 + 12345
+    col2.add_to_distributions({"x": x[:half]})
+    col2.add_to_distributions({"x": x[half:]})
+    assert torch.equal(col2._hist, whole)
+
+
+# ---------------------------------------------------------------------- a5 - a7
+def test_kl_search_vs_golden(cq):
+    g = load_golden("kl.npz")
+    names = sorted(k[:-3] for k in g.files if k.endswith("/kl"))
+    meta = _meta(g)
+    dists, intervals = {}, {}
+    for n in names:
+        dists[n] = g[n + "/counts"]
+        iv = g[n + "/interval"][0]
+        intervals[n] = np.float32(iv) if meta[n]["interval_type"] == "float32" else float(iv)
+    q = cq.Quantizer(names, worker_num=4, keep_curves=True)
+    q.quantize(dists, intervals)
+    curves = q.kl_curves.cpu().numpy()
+    for i, n in enumerate(names):
+        ref = g[n + "/kl"]
+        np.testing.assert_allclose(curves[i], ref, rtol=1e-9, atol=1e-300, err_msg=n)
+        best, t_ref = 66666, 2047
+        for j, v in enumerate(ref):
+            if v < best:
+                best, t_ref = v, 128 + j
+        assert q.threshold_bin[n] == t_ref, n
+        assert q.bits[n] == int(g[n + "/bit"][0]), n
+        assert float(q.threshold_value[n]) == float(g[n + "/threshold_value"][0]), n
+
+
+def test_kl_search_vs_oracle_random(cq, oracle):
+    rng = np.random.default_rng(5)
+    names, dists, intervals = [], {}, {}
+    for i in range(24):
+        sigma = rng.uniform(60, 900)
+        x = np.abs(rng.normal(0, sigma, size=rng.integers(1000, 400000)))
+        h = np.bincount(np.minimum(x.astype(np.int64), 2047), minlength=2048).astype(np.int32)
+        if i % 5 == 0:
+            h[rng.integers(0, 2048, size=600)] = 0
+        n = "t%d" % i
+        names.append(n)
+        dists[n] = h
+        intervals[n] = np.float32(rng.uniform(1e-4, 0.1))
+    q = cq.Quantizer(names, keep_curves=True)
+    q.quantize(dists, intervals)
+    curves = q.kl_curves.cpu().numpy()
+    for i, n in enumerate(names):
+        t, kl = oracle.kl_search(oracle.normalize(dists[n]))
+        np.testing.assert_allclose(curves[i], kl, rtol=1e-9, atol=1e-300)
+        assert q.threshold_bin[n] == t
+        assert q.bits[n] == oracle.threshold_to_bit(t, intervals[n])[0]
+
+
+# --------------------------------------------------------------------- a10 / a12
+@pytest.mark.parametrize("bit", gg.FQ_BITS)
+def test_fakequant_vs_golden(cq, bit):
+    g = load_golden("fakequant.npz")
+    x = gg.fakequant_inputs()
+    y = cq.QuanDequan(8, bit)(dev(x)).cpu().numpy()
+    ref = g["y_bit%d" % bit]
+    assert np.array_equal(y, ref)
+    assert np.array_equal(np.signbit(y), np.signbit(ref))
+    q = cq.Quantity(bit)(dev(x)).cpu().numpy()
+    assert np.array_equal(q, g["q_bit%d" % bit])
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 1023, 1 << 20, (1 << 22) + 3])
+def test_fakequant_sizes_vs_oracle(cq, oracle, n):
+    x = det_inputs.bell(n, 123, 30.0)
+    for bit in (-2, 3, 7):
+        y = cq.QuanDequan(8, bit)(dev(x)).cpu().numpy()
+        assert np.array_equal(y, oracle.fakequant(x, bit))
+    t = dev(np.concatenate([np.zeros(1, np.float32), x]))[1:]       # unaligned view
+    assert np.array_equal(cq.QuanDequan(8, 5)(t).cpu().numpy(), oracle.fakequant(x, 5))
+
+
+def test_fakequant_full_size_properties(cq):
+    """C2-scale tensor: idempotence, range and grid membership; equality with the 4 ATen ops."""
+    n = 636_000_000 // 4
+    x = torch.randn(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9)) * 3
+    op = cq.QuanDequan(8, 4)
+    y = op(x)
+    assert torch.equal(op(y), y)
+    assert float(y.max()) <= 127 / 16 and float(y.min()) >= -128 / 16
+    assert torch.equal(y * 16, torch.round(y * 16))
+    ref = torch.div(torch.round(torch.mul(x, 16)).clamp(-128, 127), 16)
+    assert torch.equal(y, ref)
+
+
+# ---------------------------------------------------------------------- a14 / a15
+def test_rshift_add_standalone_vs_golden(cq, oracle):
+    g = load_golden("intsim.npz")
+    accs = np.arange(-1100, 1100, dtype=np.float32)
+    for rs in (-2, 0, 1, 3, 7):
+        y = cq.RightShift(8, rs)(dev(accs)).cpu().numpy()
+        assert np.array_equal(y, g["rshift/rs%d" % rs])
+    a, c = det_inputs.bell(4096, 41, 60.0), det_inputs.bell(4096, 42, 60.0)
+    assert np.array_equal(cq.NewAdd()(dev(a), dev(c)).cpu().numpy(), g["add/y"])
+    x = det_inputs.bell(5000, 43, 100.0)
+    assert np.array_equal(cq.Sp(8)(dev(x)).cpu().numpy(), np.clip(x, -128, 127))
+    assert np.array_equal(cq.DeQuantity(5)(dev(x)).cpu().numpy(), x / np.float32(32))
+
+
+def test_quantize_nchw_to_nhwc(cq, oracle):
+    from common.quantity import _native
+    for (N, C, H, W, cpad) in [(2, 3, 9, 7, 16), (1, 64, 5, 5, 64), (3, 24, 11, 13, 32), (2, 130, 4, 4, 144)]:
+        x = det_inputs.bell(N * C * H * W, 50 + C, 4.0).reshape(N, C, H, W)
+        q = _native.quantize_nchw_to_nhwc_s8(dev(x), 4, cpad).cpu().numpy()
+        ref = np.zeros((N, H, W, cpad), np.int8)
+        ref[..., :C] = oracle.quantize_input(x, 4).transpose(0, 2, 3, 1).astype(np.int8)
+        assert np.array_equal(q, ref)
+
+
+# ------------------------------------------------------------------ C-ABI behaviour
+def test_abi_error_codes(cq):
+    import ctypes
+    from common.quantity import _native
+    lib = _native.lib()
+    assert lib.pq_fakequant_f32(None, None, 10, 0, -128.0, 127.0, 1, None) == -1
+    x = torch.zeros(8, device="cuda")
+    assert lib.pq_fakequant_f32(x.data_ptr(), x.data_ptr(), 8, 0, -128.0, 127.0, 1, None) == -1   # aliasing
+    assert lib.pq_fakequant_f32(x.data_ptr(), x.data_ptr(), 0, 0, -128.0, 127.0, 1, None) == 0    # empty
+    k = _native.MAX_SEGMENTS + 1
+    ptrs = (ctypes.c_void_p * k)(*([x.data_ptr()] * k))
+    ns = (ctypes.c_uint64 * k)(*([8] * k))
+    out = torch.zeros(k, dtype=torch.int32, device="cuda")
+    assert lib.pq_absmax_multi_f32(ptrs, ns, k, out.data_ptr(), None) == -4
+    iv = (ctypes.c_float * 1)(0.0)
+    h = torch.zeros(2048, dtype=torch.int64, device="cuda")
+    assert lib.pq_hist2048_multi_f32(ptrs, ns, iv, 1, h.data_ptr(), None) == -1                  # interval <= 0
+    with pytest.raises(RuntimeError):
+        cq.QuanDequan(8, 3)(torch.zeros(4))                                                       # CPU tensor: no fallback

@@ -1,0 +1,128 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares,
+host-side logic (JSON writer, re-writer, bit reader, graph pruning / merge groups) agrees
+with the reference's golden outputs.  No compute kernels are launched."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, REPO, golden_json, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    from common.quantity import _native
+    header = open(os.path.join(REPO, "include", "pq_sm100.h")).read()
+    declared = set(re.findall(r"\b(pq_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
+    lib = _native.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pq_version() >= 100
+    assert b"PQ_EINVAL" in lib.pq_error_string(-1)
+    assert lib.pq_kl_workspace_doubles() >= 2048 + 2 * 1920
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(REPO, "pytorch-quantity_b200")
+    for root, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert "oracle" not in text.replace("# oracle-free", ""), os.path.join(root, f)
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    import common.quantity as cq
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError):
+        cq.QuanDequan(8, 3)(torch.zeros(4))
+    with pytest.raises(RuntimeError):
+        cq.DistributionCollector(["a"]).refresh_max_val({"a": np.zeros(4, np.float32)})
+    with pytest.raises(RuntimeError):
+        cq.Quantizer(["a"]).quantize({"a": np.ones(2048, np.int32)}, {"a": np.float32(0.1)})
+
+
+def test_json_writer_is_byte_identical_to_json_dump():
+    from tools._jsonio import dumps_int_array
+    rng = np.random.default_rng(0)
+    for shape in [(5,), (3, 4), (2, 3, 3, 3), (4, 1, 1, 1), (1,), (2, 0), (7, 2, 1)]:
+        a = rng.integers(-128, 128, size=shape).astype(np.int32)
+        assert dumps_int_array(a) == json.dumps(a.tolist(), indent=4), shape
+    a8 = rng.integers(-128, 128, size=(3, 2)).astype(np.int8)
+    assert dumps_int_array(a8) == json.dumps(a8.tolist(), indent=4)
+
+
+def test_rewriter_and_bit_reader_vs_golden(tmp_path):
+    """BiasReWriter on a hand-computed case: bias alignment, int8 wrap-around (quirk Q8),
+    MAX_SHIFT cap, table rewrite (tools/rewriter.py:38-140).  The reference-produced files are
+    compared byte-for-byte in tests/test_gpu_e2e.py."""
+    from common.quantity import BitReader
+    from tools import BiasReWriter
+    from tools._jsonio import dump_int_array
+    wd = tmp_path
+    for sub in ("weight", "bias", "new_weight", "new_bias"):
+        os.makedirs(wd / sub)
+    old_bias = {"a": 3, "b": 9}
+    new_bias = {"a": 5, "b": 4}
+    dump_int_array(np.array([100, -100, 50, 1], np.int32), str(wd / "bias" / "a.bias.json"))
+    dump_int_array(np.array([100, -100, 48, 16, 24, 8], np.int32), str(wd / "bias" / "b.bias.json"))
+    open(wd / "weight.table", "w").write("a.weight 7\na.bias 3\nb.weight 14\nb.bias 9\n")
+    open(wd / "feat.table", "w").write("image 4\na 5 4\nb 4 5\n")
+    dump_int_array(np.array([[100, -100], [3, 127]], np.int32), str(wd / "weight" / "a.weight.json"))
+    dump_int_array(np.array([[64, -128], [2, 6]], np.int32), str(wd / "weight" / "b.weight.json"))
+    rw = BiasReWriter(str(wd / "weight"), str(wd / "bias"), str(wd / "new_weight"), str(wd / "new_bias"),
+                      str(wd / "weight.table"), str(wd / "feat.table"), max_shift_limit=12)
+    wb, bb = rw.get_weight_info()
+    fb, ib = rw.get_feat_info()
+    assert dict(wb) == {"a": 7, "b": 14} and dict(bb) == old_bias and fb == {"image": 4, "a": 5, "b": 4}
+    rw.rewrite_bias_table(bb, fb)
+    rw.rewrite_bias_dir(bb, fb)
+    assert json.load(open(wd / "new_bias" / "a.bias.json")) == [-112, 112, -56, 4]      # x4, int8 wrap (quirk Q8)
+    assert json.load(open(wd / "new_bias" / "b.bias.json")) == [3, -3, 2, 0, 1, 0]      # /32, half-even
+    need, nw = rw.max_shift_limit_weight(fb, ib, wb)
+    assert need and nw == {"a": 7, "b": 11}                                             # 14+5-4=15 > 12 -> 11
+    rw.rewrite_weight_table(wb, nw)
+    rw.rewrite_weight_dir(wb, nw)
+    assert open(wd / "weight.table").read() == "a.weight 7\na.bias 5\nb.weight 11\nb.bias 4\n"
+    assert json.load(open(wd / "new_weight" / "b.weight.json")) == [[8, -16], [0, 1]]
+    r = BitReader(feat_table=str(wd / "feat.table"), weight_table=str(wd / "weight.table"))
+    assert r.get_feat_info()[1]["b"] == ["5"]
+
+
+def test_graph_pruning_and_merge_groups_host_logic():
+    """prune_net_info / get_merge_groups on the reference's own un-pruned trace of the tiny net."""
+    from collections import OrderedDict
+    from tools.pytorch_quantizer import Quantity
+    g = load_golden("tiny_e2e.npz")
+    j = golden_json(g)
+    q = object.__new__(Quantity)
+    q._cared_op_type = ["Conv2d", "Linear", "Eltwise", "Concat"]
+    q._merge_op_type = ["Eltwise", "Concat"]
+    q.verbose, q.rank = False, 0
+    full = OrderedDict([
+        ("Conv2d_1", {"inputs": [], "type": "Conv2d"}),
+        ("ReLU_2", {"inputs": ["Conv2d_1"], "type": "ReLU"}),
+        ("MaxPool2d_3", {"inputs": ["ReLU_2"], "type": "MaxPool2d"}),
+        ("Conv2d_4", {"inputs": ["MaxPool2d_3"], "type": "Conv2d"}),
+        ("Conv2d_5", {"inputs": ["MaxPool2d_3"], "type": "Conv2d"}),
+        ("Concat_6", {"inputs": ["Conv2d_4", "Conv2d_5"], "type": "Concat"}),
+        ("ReLU_7", {"inputs": ["Concat_6"], "type": "ReLU"}),
+        ("Conv2d_8", {"inputs": ["ReLU_7"], "type": "Conv2d"}),
+        ("Eltwise_9", {"inputs": ["Conv2d_8", "MaxPool2d_3"], "type": "Eltwise"}),
+        ("ReLU_10", {"inputs": ["Eltwise_9"], "type": "ReLU"}),
+        ("Conv2d_11", {"inputs": ["ReLU_10"], "type": "Conv2d"}),
+        ("Eltwise_12", {"inputs": ["Conv2d_11", "ReLU_10"], "type": "Eltwise"}),
+        ("ReLU_13", {"inputs": ["Eltwise_12"], "type": "ReLU"}),
+        ("AvgPool2d_14", {"inputs": ["ReLU_13"], "type": "AvgPool2d"}),
+        ("View_15", {"inputs": ["AvgPool2d_14"], "type": "View"}),
+        ("Linear_16", {"inputs": ["View_15"], "type": "Linear"}),
+    ])
+    keep = [n for n, i in full.items() if i["type"] in q._cared_op_type]
+    pruned = q.prune_net_info(full, keep)
+    assert pruned == j["net_info"] and list(pruned) == list(j["net_info"])
+    assert q.get_merge_groups(pruned) == j["merge_groups"]
