@@ -177,7 +177,7 @@ def ours(args):
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.backends.cudnn.allow_tf32 = False           # the forward stays true fp32, like the reference
     torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = os.environ.get("PQ_BENCH_NO_AUTOTUNE") != "1"   # off under ncu
     _native.lib()
     net = build_model()
     workdir = os.path.join("/tmp", "pq_bench_rank%d" % rank)

@@ -103,6 +103,10 @@ def _pad16(c):
     return (c + 15) // 16 * 16
 
 
+def _pad32(c):
+    return (c + 31) // 32 * 32
+
+
 class _IntSimBase(nn.Module):
     def _read_info(self, quantize_infor):
         self.weight_bit = quantize_infor["weight_bit"]
@@ -153,7 +157,9 @@ class NewConv2d(_IntSimBase):
             raise NotImplementedError("NewConv2d: groups=1, dilation=1, zero padding only")
         wq = self._quantize_params(conv, conv.out_channels)
         K, C, R, S = wq.shape
-        self._c_pad = _pad16(C)
+        # im2col TMA fetches channel blocks of 32 / 64 / 128 bytes; a 1x1 stride-1 conv is a plain GEMM
+        plain = (R, S) == (1, 1) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (0, 0)
+        self._c_pad = _pad16(C) if plain else _pad32(C)
         w_krsc = torch.zeros((K, R, S, self._c_pad), dtype=torch.int8, device=wq.device)
         w_krsc[..., :C] = wq.permute(0, 2, 3, 1).to(torch.int8)
         self.register_buffer("_w_krsc", w_krsc.contiguous())

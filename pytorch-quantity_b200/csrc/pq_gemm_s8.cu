@@ -1,13 +1,476 @@
-// pq_gemm_s8.cu -- placeholder until the tcgen05 int8 GEMM / implicit-GEMM conv lands.
+// pq_gemm_s8.cu -- ReconModel integer simulation (subsystem 4):
+// int8 x int8 -> int32 GEMM and implicit-GEMM convolution on the 5th-generation tensor cores
+// (tcgen05.mma kind::i8, accumulators in TMEM), operands staged by TMA, with the reference's
+//   RightShift -> BiasAdd -> Sp -> DeQuantity        (new_quantity_op.py:11-44, 61-101, 124-133)
+// chain fused into the epilogue.
+//
+// One CTA computes one 128 x BN output tile:
+//   warp 0   : TMA producer.  A tile = 128 output pixels x BK input channels of ONE filter tap,
+//              fetched by a single im2col-mode TMA (padding = hardware zero fill, stride =
+//              traversal stride), or a plain 2-D tile for GEMMs / 1x1 stride-1 convolutions.
+//              B tile = BN filters x the same BK-byte slice of the [K][R*S*C] weight matrix.
+//   warp 1   : allocates TMEM, issues tcgen05.mma (one elected lane), commits to mbarriers.
+//   warps 2-5: epilogue.  tcgen05.ld the int32 accumulators (lane = output pixel, column = output
+//              channel), shift / round-half-away / saturate, + bias, saturate, then either
+//              de-quantise to fp32 NCHW (the module boundary of the reference) or store int8 NHWC.
+// A STAGES-deep mbarrier ring decouples the three roles; two CTAs fit per SM so one tile's
+// epilogue overlaps the other's main loop.
+#include <cuda.h>
+
 #include "pq_common.cuh"
 
-extern "C" int pq_gemm_s8(const int8_t *, const int8_t *, const int32_t *, int, int, int, int, int, int,
-                          float *, int8_t *, pq_stream_t)
+namespace pq {
+
+constexpr int kBM = 128;               // UMMA M (cta_group::1): one TMEM lane per output row
+constexpr int kGemmThreads = 192;      // 6 warps: TMA, MMA, 4 x epilogue
+
+// ------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-    return PQ_EUNSUPPORTED;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-extern "C" int pq_conv2d_s8(const int8_t *, const int8_t *, const int32_t *, const pq_conv_desc *, float *,
-                            int8_t *, pq_stream_t)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
-    return PQ_EUNSUPPORTED;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], int8 operands, int32 accumulate
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory operand descriptor (cute::UMMA::SmemDescriptor): rows of BK bytes, swizzle
+// span == BK, 8-row groups SBO = 8*BK bytes apart; version 1 (Blackwell).
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
+{
+    constexpr uint64_t layout = BK == 128 ? 2 : (BK == 64 ? 4 : 6);      // SWIZZLE_128B / 64B / 32B
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);                          // start address
+    d |= (uint64_t)1 << 16;                                              // LBO (unused for swizzled K-major)
+    d |= (uint64_t)((8 * BK) >> 4) << 32;                                // SBO
+    d |= (uint64_t)1 << 46;                                              // descriptor version
+    d |= layout << 61;
+    return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::i8: S32 accumulate, signed A and B, both K-major.
+__host__ __device__ constexpr uint32_t make_idesc_i8(int m, int n)
+{
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct GemmParams {
+    int M, N;                  // output rows (pixels) and columns (channels)
+    int num_kb;                // K blocks of BK bytes
+    int a_im2col;              // 0: A is a 2-D [M][K] tile source; 1: im2col over NHWC
+    int R, S, cblocks;         // filter taps and BK-blocks per tap (im2col mode)
+    int C;                     // padded channels (bytes per pixel)
+    int P, Q;                  // output height / width (im2col mode)
+    int stride_h, stride_w, pad_h, pad_w;
+    int rs, ob;                // RightShift amount, output fractional bit
+    int hw;                    // pixels per image for the fp32 NCHW store (1: plain [M][N])
+    const int32_t *bias;       // [N] quantised bias (already saturated to int8 range)
+    float *out_f32;            // optional
+    int8_t *out_s8;            // optional, [M][N]
+};
+
+// RightShift (round half away from zero, saturate) + BiasAdd + Sp, all in integers.
+__device__ __forceinline__ int requant(int acc, int rs, int bias)
+{
+    int r;
+    if (rs >= 1) {
+        const int a = acc < 0 ? -acc : acc;
+        const int mag = rs > 30 ? 0 : (int)(((unsigned int)a + (1u << (rs - 1))) >> rs);
+        r = acc < 0 ? -mag : mag;
+        r = max(-128, min(127, r));
+    } else {
+        r = max(-128, min(127, acc));                 // saturate first: the left shift is monotone
+        r = max(-128, min(127, r * (1 << (-rs > 8 ? 8 : -rs))));
+    }
+    return max(-128, min(127, r + bias));
+}
+
+template <int BN, int BK, int STAGES>
+struct GemmSmem {
+    static constexpr int kABytes = kBM * BK;
+    static constexpr int kBBytes = BN * BK;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr size_t kTotal = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + 256 /*barriers*/;
+};
+
+template <int BN, int BK, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmParams p)
+{
+    using Cfg = GemmSmem<BN, BK, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + (size_t)STAGES * Cfg::kABytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * Cfg::kStageBytes);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+    constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int wq = 0, hp = 0, nb = 0;
+            if (p.a_im2col) {                          // first output pixel of the tile -> input coords
+                const int pq = p.P * p.Q;
+                nb = m0 / pq;
+                const int rem = m0 - nb * pq;
+                hp = rem / p.Q;
+                wq = rem - hp * p.Q;
+            }
+            int stage = 0; uint32_t phase = 0;
+            int r = 0, s = 0, cb = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(empty_bar + stage, phase ^ 1);
+                mbar_expect_tx(full_bar + stage, Cfg::kStageBytes);
+                void *dst_a = smem_a + (size_t)stage * Cfg::kABytes;
+                void *dst_b = smem_b + (size_t)stage * Cfg::kBBytes;
+                if (p.a_im2col) {
+                    tma_load_im2col_4d(&tmap_a, full_bar + stage, dst_a, cb * BK, wq * p.stride_w - p.pad_w,
+                                       hp * p.stride_h - p.pad_h, nb, (uint16_t)s, (uint16_t)r);
+                    tma_load_2d(&tmap_b, full_bar + stage, dst_b, (r * p.S + s) * p.C + cb * BK, n0);
+                    if (++cb == p.cblocks) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
+                } else {
+                    tma_load_2d(&tmap_a, full_bar + stage, dst_a, kb * BK, m0);
+                    tma_load_2d(&tmap_b, full_bar + stage, dst_b, kb * BK, n0);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_i8(kBM, BN < 16 ? 16 : BN);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(full_bar + stage, phase);
+                tc_fence_after();
+                const uint64_t da = make_smem_desc<BK>(smem_u32(smem_a + (size_t)stage * Cfg::kABytes));
+                const uint64_t db = make_smem_desc<BK>(smem_u32(smem_b + (size_t)stage * Cfg::kBBytes));
+#pragma unroll
+                for (int k = 0; k < BK / 32; ++k)      // UMMA_K = 32 int8: advance 32 B inside the swizzle span
+                    umma_i8(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                umma_commit(empty_bar + stage);        // frees the smem slot when these MMAs retire
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tmem_full_bar);                // accumulator complete
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;
+        const int m = m0 + row;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const float dq = __int_as_float((127 - p.ob) << 23);        // 2^-ob, exact
+        long long img = 0; int pix = 0;
+        if (p.hw > 1) { img = m / p.hw; pix = m - (int)img * p.hw; }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            if (n0 + c0 >= p.N) break;
+            uint32_t acc[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, acc);
+            if (m < p.M) {
+                int y[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c0 + j;
+                    y[j] = requant((int)acc[j], p.rs, n < p.N ? __ldg(p.bias + n) : 0);
+                }
+                if (p.out_f32) {
+                    if (p.hw > 1) {                    // NCHW: lanes of a warp write consecutive pixels
+                        float *o = p.out_f32 + ((size_t)img * p.N + n0 + c0) * p.hw + pix;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + c0 + j < p.N) o[(size_t)j * p.hw] = __fmul_rn((float)y[j], dq);
+                    } else {
+                        float *o = p.out_f32 + (size_t)m * p.N + n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + c0 + j < p.N) o[j] = __fmul_rn((float)y[j], dq);
+                    }
+                }
+                if (p.out_s8) {
+                    int8_t *o = p.out_s8 + (size_t)m * p.N + n0 + c0;
+                    if (n0 + c0 + 16 <= p.N && (p.N & 15) == 0) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            w[j] = (uint32_t)(y[4 * j] & 0xff) | ((uint32_t)(y[4 * j + 1] & 0xff) << 8) |
+                                   ((uint32_t)(y[4 * j + 2] & 0xff) << 16) | ((uint32_t)(y[4 * j + 3] & 0xff) << 24);
+                        *reinterpret_cast<uint4 *>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + c0 + j < p.N) o[j] = (int8_t)y[j];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace pq
+
+// ------------------------------------------------------------------------------------ host side
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const int *, const int *, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+
+int load_driver_entry_points()
+{
+    if (g_encode_tiled && g_encode_im2col) return PQ_OK;
+    cudaDriverEntryPointQueryResult q;
+    void *fn = nullptr;
+    PQ_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !fn) return PQ_EUNSUPPORTED;
+    g_encode_tiled = (EncodeTiledFn)fn;
+    PQ_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !fn) return PQ_EUNSUPPORTED;
+    g_encode_im2col = (EncodeIm2colFn)fn;
+    return PQ_OK;
+}
+
+CUtensorMapSwizzle swizzle_for(int bk)
+{
+    return bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// 2-D K-major int8 matrix [rows][k_bytes] (row pitch `pitch` bytes) -> box [box_rows][bk]
+int encode_2d(CUtensorMap *map, const void *base, uint64_t k_bytes, uint64_t rows, uint64_t pitch, int bk,
+              int box_rows)
+{
+    cuuint64_t dims[2] = {k_bytes, rows};
+    cuuint64_t strides[1] = {pitch};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk),
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PQ_OK : PQ_EUNSUPPORTED;
+}
+
+int encode_im2col(CUtensorMap *map, const void *base, const pq_conv_desc &d, int bk)
+{
+    cuuint64_t dims[4] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
+    cuuint64_t strides[3] = {(cuuint64_t)d.C, (cuuint64_t)d.W * d.C, (cuuint64_t)d.H * d.W * d.C};
+    int lower[2] = {-d.pad_w, -d.pad_h};
+    int upper[2] = {d.pad_w - (d.S - 1), d.pad_h - (d.R - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d.stride_w, (cuuint32_t)d.stride_h, 1};
+    CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), dims, strides,
+                                 lower, upper, (cuuint32_t)bk, (cuuint32_t)pq::kBM, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return PQ_EUNSUPPORTED;
+    // Same work-around CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp) for drivers <= 13.1:
+    // small tensors must not carry the bit the encoder sets for them.
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && (uint64_t)d.N * d.H * d.W * d.C < 131072) reinterpret_cast<uint64_t *>(map)[1] &= ~(1ull << 21);
+    return PQ_OK;
+}
+
+template <int BN, int BK, int STAGES>
+int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, const pq::GemmParams &p, cudaStream_t s)
+{
+    using Cfg = pq::GemmSmem<BN, BK, STAGES>;
+    auto kern = pq::gemm_s8_kernel<BN, BK, STAGES>;
+    static bool attr = false;
+    if (!attr) {
+        PQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kTotal));
+        attr = true;
+    }
+    dim3 grid((p.M + pq::kBM - 1) / pq::kBM, (p.N + BN - 1) / BN);
+    kern<<<grid, pq::kGemmThreads, Cfg::kTotal, s>>>(ta, tb, p);
+    return (int)cudaGetLastError();
+}
+
+template <int BK>
+int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, const pq::GemmParams &p, int bn, cudaStream_t s)
+{
+    constexpr int S128 = BK == 128 ? 3 : (BK == 64 ? 6 : 8);
+    constexpr int S64 = BK == 128 ? 4 : 8;
+    switch (bn) {
+        case 128: return launch_cfg<128, BK, S128>(ta, tb, p, s);
+        case 64: return launch_cfg<64, BK, S64>(ta, tb, p, s);
+        default: return launch_cfg<32, BK, 8>(ta, tb, p, s);
+    }
+}
+
+int pick_bn(int n) { return n > 64 ? 128 : (n > 32 ? 64 : 32); }
+
+int launch(const CUtensorMap &ta, const CUtensorMap &tb, const pq::GemmParams &p, int bk, int bn, cudaStream_t s)
+{
+    switch (bk) {
+        case 128: return launch_bn<128>(ta, tb, p, bn, s);
+        case 64: return launch_bn<64>(ta, tb, p, bn, s);
+        default: return launch_bn<32>(ta, tb, p, bn, s);
+    }
+}
+
+}  // namespace
+
+extern "C" int pq_gemm_s8(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs,
+                          int ob, int hw, float *out_f32, int8_t *out_s8, pq_stream_t stream)
+{
+    if (M <= 0 || N <= 0 || K <= 0 || hw <= 0) return PQ_EINVAL;
+    if (!a || !w || !bias_q || (!out_f32 && !out_s8)) return PQ_EINVAL;
+    if ((K & 15) || (((uintptr_t)a | (uintptr_t)w) & 15)) return PQ_EALIGN;
+    if (ob < -100 || ob > 100 || (hw > 1 && M % hw)) return PQ_EUNSUPPORTED;
+    int rc = load_driver_entry_points();
+    if (rc != PQ_OK) return rc;
+    const int bk = K >= 128 ? 128 : (K >= 64 ? 64 : 32);
+    const int bn = pick_bn(N);
+    CUtensorMap ta, tb;
+    if ((rc = encode_2d(&ta, a, K, M, K, bk, pq::kBM)) != PQ_OK) return rc;
+    if ((rc = encode_2d(&tb, w, K, N, K, bk, bn)) != PQ_OK) return rc;
+    pq::GemmParams p = {};
+    p.M = M; p.N = N; p.num_kb = (K + bk - 1) / bk; p.a_im2col = 0;
+    p.rs = rs; p.ob = ob; p.hw = hw; p.bias = bias_q; p.out_f32 = out_f32; p.out_s8 = out_s8;
+    return launch(ta, tb, p, bk, bn, (cudaStream_t)stream);
+}
+
+extern "C" int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
+                            const pq_conv_desc *desc_host, float *out_f32_nchw, int8_t *out_s8_nhwc,
+                            pq_stream_t stream)
+{
+    if (!x_nhwc || !w_krsc || !bias_q || !desc_host || (!out_f32_nchw && !out_s8_nhwc)) return PQ_EINVAL;
+    const pq_conv_desc &d = *desc_host;
+    if (d.N <= 0 || d.H <= 0 || d.W <= 0 || d.C <= 0 || d.K <= 0 || d.R <= 0 || d.S <= 0) return PQ_EINVAL;
+    if (d.stride_h <= 0 || d.stride_w <= 0 || d.pad_h < 0 || d.pad_w < 0) return PQ_EINVAL;
+    if (d.P != (d.H + 2 * d.pad_h - d.R) / d.stride_h + 1 || d.Q != (d.W + 2 * d.pad_w - d.S) / d.stride_w + 1)
+        return PQ_EINVAL;
+    if ((d.C & 15) || (((uintptr_t)x_nhwc | (uintptr_t)w_krsc) & 15)) return PQ_EALIGN;
+    if (d.ob < -100 || d.ob > 100 || d.stride_h > 8 || d.stride_w > 8) return PQ_EUNSUPPORTED;
+    const long long M = (long long)d.N * d.P * d.Q;
+    if (M > 0x7fffffffLL) return PQ_EUNSUPPORTED;
+    if (d.R == 1 && d.S == 1 && d.stride_h == 1 && d.stride_w == 1 && d.pad_h == 0 && d.pad_w == 0)
+        return pq_gemm_s8(x_nhwc, w_krsc, bias_q, (int)M, d.K, d.C, d.rs, d.ob, d.P * d.Q, out_f32_nchw,
+                          out_s8_nhwc, stream);                      // 1x1 stride-1: a plain GEMM over NHWC
+    if (d.C & 31) return PQ_EUNSUPPORTED;                            // im2col path: channel blocks of >= 32
+    int rc = load_driver_entry_points();
+    if (rc != PQ_OK) return rc;
+    const int bk = (d.C % 128 == 0) ? 128 : ((d.C % 64 == 0) ? 64 : 32);
+    const int bn = pick_bn(d.K);
+    CUtensorMap ta, tb;
+    if ((rc = encode_im2col(&ta, x_nhwc, d, bk)) != PQ_OK) return rc;
+    const uint64_t ktot = (uint64_t)d.R * d.S * d.C;
+    if ((rc = encode_2d(&tb, w_krsc, ktot, d.K, ktot, bk, bn)) != PQ_OK) return rc;
+    pq::GemmParams p = {};
+    p.M = (int)M; p.N = d.K; p.a_im2col = 1;
+    p.R = d.R; p.S = d.S; p.C = d.C; p.cblocks = d.C / bk; p.num_kb = d.R * d.S * p.cblocks;
+    p.P = d.P; p.Q = d.Q; p.stride_h = d.stride_h; p.stride_w = d.stride_w; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
+    p.rs = d.rs; p.ob = d.ob; p.hw = d.P * d.Q; p.bias = bias_q; p.out_f32 = out_f32_nchw; p.out_s8 = out_s8_nhwc;
+    return launch(ta, tb, p, bk, bn, (cudaStream_t)stream);
 }

@@ -1,0 +1,122 @@
+"""GPU parity of the integer simulation (ReconModel): tcgen05 int8 GEMM / implicit-GEMM conv with
+the fused shift-round-saturate-bias epilogue, through the C ABI, against the reference's golden
+outputs (tests/golden/intsim.npz, tiny_e2e.npz) and the oracle.  Bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import det_inputs
+from conftest import golden_json, load_golden
+from golden import gen_golden as gg
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (1, 16, 16), (5, 10, 512), (300, 64, 48), (257, 1000, 208),
+                                   (1000, 72, 2048), (4096, 256, 64), (129, 33, 32)])
+@pytest.mark.parametrize("rs", [7, 0, -1])
+def test_gemm_s8_vs_oracle(oracle, M, N, K, rs):
+    from common.quantity import _native
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    a = rng.integers(-128, 128, size=(M, K), dtype=np.int8)
+    w = rng.integers(-128, 128, size=(N, K), dtype=np.int8)
+    b = rng.integers(-128, 128, size=N).astype(np.int32)
+    scale = 1 if rs > 0 else 64          # keep some results inside the clamp range when rs <= 0
+    a = (a // scale).astype(np.int8); w = (w // scale).astype(np.int8)
+    acc = a.astype(np.int64) @ w.astype(np.int64).T
+    y = np.clip(oracle.right_shift(acc, rs) + b[None, :], -128, 127)
+    ob = 3
+    f32, s8 = _native.gemm_s8(dev(a), dev(w), dev(b), rs, ob, want_f32=True, want_s8=True)
+    assert np.array_equal(s8.cpu().numpy().astype(np.int64), y)
+    assert np.array_equal(f32.cpu().numpy(), (y / 8.0).astype(np.float32))
+
+
+@pytest.mark.parametrize("case", gg.INTSIM_CONV_CASES, ids=[c[0] for c in gg.INTSIM_CONV_CASES])
+def test_newconv2d_vs_golden(case):
+    import common.quantity as cq
+    g = load_golden("intsim.npz")
+    name, B, Cin, H, W, Cout, k, stride, pad = case[:9]
+    x, w, b, info = gg.intsim_conv_tensors(case)
+    conv = nn.Conv2d(Cin, Cout, k, stride=stride, padding=pad, bias=b is not None)
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(w))
+        if b is not None:
+            conv.bias.copy_(torch.from_numpy(b))
+        m = cq.NewConv2d(conv.cuda(), dict(info))
+        y = m(dev(x))
+    assert np.array_equal(m.Conv.weight.data.cpu().numpy().astype(np.int8), g["conv/" + name + "/wq"])
+    assert np.array_equal(m.quantized_bias.cpu().numpy().astype(np.int32), g["conv/" + name + "/bq"])
+    assert y.shape == g["conv/" + name + "/y"].shape
+    assert np.array_equal(y.cpu().numpy(), g["conv/" + name + "/y"])
+
+
+@pytest.mark.parametrize("case", gg.INTSIM_LINEAR_CASES, ids=[c[0] for c in gg.INTSIM_LINEAR_CASES])
+def test_newlinear_vs_golden(case):
+    import common.quantity as cq
+    g = load_golden("intsim.npz")
+    name, B, fin, fout = case[:4]
+    x, w, b, info = gg.intsim_linear_tensors(case)
+    lin = nn.Linear(fin, fout)
+    with torch.no_grad():
+        lin.weight.copy_(torch.from_numpy(w)); lin.bias.copy_(torch.from_numpy(b))
+        y = cq.NewLinear(lin.cuda(), dict(info))(dev(x))
+    assert np.array_equal(y.cpu().numpy(), g["linear/" + name + "/y"])
+
+
+# ResNet-50 layer geometries at a small batch: (Cin, H, W, Cout, k, stride, pad)
+R50_SHAPES = [(3, 56, 56, 64, 7, 2, 3), (64, 28, 28, 64, 1, 1, 0), (64, 28, 28, 64, 3, 1, 1),
+              (256, 28, 28, 512, 1, 2, 0), (128, 28, 28, 128, 3, 2, 1), (256, 14, 14, 256, 3, 1, 1),
+              (512, 7, 7, 2048, 1, 1, 0), (512, 7, 7, 512, 3, 1, 1), (1024, 14, 14, 2048, 1, 2, 0)]
+
+
+@pytest.mark.parametrize("shape", R50_SHAPES, ids=["%dx%dx%d_k%d_s%d" % (s[0], s[1], s[3], s[4], s[5]) for s in R50_SHAPES])
+def test_conv_s8_resnet50_geometries_vs_oracle(oracle, shape):
+    import common.quantity as cq
+    Cin, H, W, Cout, k, stride, pad = shape
+    B = 3
+    x = det_inputs.bell(B * Cin * H * W, 300 + Cin, 2.0).reshape(B, Cin, H, W)
+    w = det_inputs.bell(Cout * Cin * k * k, 301 + Cin, 0.05).reshape(Cout, Cin, k, k)
+    b = det_inputs.bell(Cout, 302 + Cin, 1.0)
+    info = {"weight_bit": 9, "input_bit": 5, "output_bit": 4, "bias_bit": 4}
+    conv = nn.Conv2d(Cin, Cout, k, stride=stride, padding=pad)
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(w)); conv.bias.copy_(torch.from_numpy(b))
+        y = cq.NewConv2d(conv.cuda(), dict(info))(dev(x)).cpu().numpy()
+    ref, _ = oracle.int_conv_layer(x, w, b, info, stride=stride, padding=pad)
+    assert np.array_equal(y, ref)
+
+
+def test_tiny_reconmodel_bit_exact(tmp_path):
+    """ReconModel of the tiny net: every NewConv2d / NewLinear / NewAdd output equals the reference's."""
+    import common.quantity as cq
+    import tools
+    from test_gpu_e2e import _configs, _tiny_model
+    g = load_golden("tiny_e2e.npz")
+    j = golden_json(g)
+    cfg, user = _configs(tmp_path, (1, 3, 16, 16), 2)
+    os.makedirs(cfg["OUTPUT"]["WORK_DIR"], exist_ok=True)
+    open(cfg["OUTPUT"]["FEAT_BIT_TABLE"], "w").write(j["after_second_rewrite"]["feat.table"])
+    open(cfg["OUTPUT"]["WEIGHT_BIT_TABLE"], "w").write(j["after_second_rewrite"]["weight.table"])
+    with torch.no_grad():
+        net = _tiny_model(g)
+        r = tools.Reconstruction(net, config=cfg)
+        r.merge_bn()
+        model = r.ReconModel(r.get_quantity_information(), str(tmp_path / "workdir" / "ReconModel.pth")).cuda()
+        outs = {}
+        for name, mod in model.named_modules():
+            if type(mod).__name__ in ("NewConv2d", "NewLinear", "NewAdd"):
+                mod.register_forward_hook(lambda m, i, o, name=name: outs.__setitem__(name, o.cpu().numpy()))
+        y = model(torch.from_numpy(g["eval_batch"]).cuda()).cpu().numpy()
+    for name, val in outs.items():
+        assert np.array_equal(val, g["ReconModel/layer/" + name]), name
+    assert np.array_equal(y, g["ReconModel/y"])
+    # the saved model loads back (classes picklable by qualified name, buffers registered)
+    loaded = torch.load(str(tmp_path / "workdir" / "ReconModel.pth"), weights_only=False)
+    assert np.array_equal(loaded.cuda()(torch.from_numpy(g["eval_batch"]).cuda()).cpu().numpy(), y)
