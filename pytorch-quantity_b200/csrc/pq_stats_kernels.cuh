@@ -108,15 +108,18 @@ absmax_multi_kernel(const __grid_constant__ SegTable tab, unsigned int *__restri
 // --------------------------------------------------------------------------- histogram
 // Bin index of the reference: idx = min((int)trunc(fl32(|x| / interval)), 2047) for x != 0, where
 // the division is IEEE round-to-nearest.  A literal __fdiv_rn costs MUFU.RCP + FCHK + 5 FFMA + a
-// slow-path call per element and caps the kernel at ~63 % of HBM bandwidth (profiles/).  The fast
-// path below is exact by construction:
-//   q0 = a * r,  e = fma(-q0, d, a),  q1 = fma(e, r, q0)     with r = RN(1/d) hoisted per tensor
-// gives |q1 - RN(a/d)| <= a few ulps (<< 2^-10 for q1 < 2048).  u = RZ(min(q1, 2047.5) + 2048) then
-// holds trunc(q1) in mantissa bits [12,23) and the first 12 fraction bits f below them.  If
-// 4 <= f < 4092, q1 is at least 2^-10 away from every integer, so trunc(RN(a/d)) == trunc(q1).
-// Otherwise (0.2 % of elements, plus every zero) the element is handed to the exact slow path,
-// which performs the real division.  (NaN inputs are undefined in the reference; here they count
-// in the top bin.)
+// slow-path call per element and caps the kernel at ~63 % of HBM bandwidth; ncu shows the kernel is
+// issue-bound, not DRAM- or atomic-bound (profiles/).  The fast path is exact by construction:
+//   q0 = RN(a * r) with r = RN(1/d) hoisted per tensor.  Both roundings are <= 2^-24 relative and
+//   Q = RN(a/d) is within 2^-24 of a/d, so |q0 - Q| <= 3 * 2^-24 * q < 3.7e-4 for q < 2048.
+//   u = RZ(min(q0, 2047.5) + 2048) holds trunc(q0) in mantissa bits [12,23) and the first 12
+//   fraction bits f below them.  If 4 <= f < 4092, q0 is >= 2^-10 = 9.8e-4 away from every
+//   integer, hence trunc(Q) == trunc(q0).
+// Otherwise (0.2 % of elements, plus every exact zero) the element is "ambiguous": the hot loop
+// still counts it in bin trunc(q0) (no select, no branch), flags its float4, and the rare redo pass
+// takes that count back and files the element with the real IEEE division.  Values at or beyond
+// the top bin clamp to 2047.5 and are counted there directly (their true quotient is > 2047).
+// NaN inputs are undefined in the reference; here they land in the top bin.
 struct HistDiv {
     float d;        // bin width
     float r;        // RN(1/d)
@@ -142,18 +145,13 @@ __device__ __forceinline__ void hist_add_exact(unsigned int *sh, float v, float 
 
 // Shared-memory layout per CTA: COPIES histograms of 2048 words, each 8 KB-aligned in the shared
 // window so that `(bits >> 10) & 0x1ffc | base` is ONE logic op, followed by one trash word per
-// CTA that absorbs the (unconditional) atomics of elements routed to the slow path.
+// CTA (used by the zero-aware variant).
 constexpr unsigned int kSlowThreshold = 0xff800000u;
 
 __device__ __forceinline__ unsigned int hist_fast_bits(float v, const HistDiv &h)
 {
-    const float a = fabsf(v);
-    const float q0 = __fmul_rn(a, h.r);
-    const float e = fmaf(-q0, h.d, a);
-    // clamp at 2047.5: anything at or beyond lands in the top bin on the fast path (its true
-    // quotient is > 2047), while [2047, 2047.5) still gets the near-integer check at 2047.0
-    const float q1 = fminf(fmaf(e, h.r, q0), 2047.5f);
-    return __float_as_uint(__fadd_rz(q1, 2048.0f));
+    const float q0 = fminf(__fmul_rn(fabsf(v), h.r), 2047.5f);
+    return __float_as_uint(__fadd_rz(q0, 2048.0f));
 }
 
 // f = bits & 0xfff must lie in [4, 4092): shift it to the top of the word and range-check
@@ -162,22 +160,41 @@ __device__ __forceinline__ bool hist_is_slow(unsigned int bits)
     return (bits * 0x100000u - 0x400000u) >= kSlowThreshold;
 }
 
-// fast path for one element: always exactly one shared atomic (no divergent region).  Returns
-// whether the element must be re-done exactly.  An exact zero always looks "slow" (q = 0 sits on an
-// integer) and is routed to the trash word; ZERO_AWARE additionally keeps it from raising the
-// redo flag (+2 instructions), which matters only for sparse tensors (post-ReLU, zero padding).
+__device__ __forceinline__ unsigned int hist_fast_addr(unsigned int bits, unsigned int base_addr)
+{
+    return ((bits >> 10) & 0x1ffcu) | base_addr;
+}
+
+// One element on the hot path: exactly one shared atomic, no divergent region.  Returns whether the
+// element is ambiguous.
+//   ZERO_AWARE == false (dense data): the ambiguous element is counted in its provisional bin; the
+//     redo pass un-counts it.
+//   ZERO_AWARE == true (a warp switches to it when exact zeros keep flagging): ambiguous elements go
+//     to the trash word instead and exact zeros do not raise the flag (+3 instructions).
 template <bool ZERO_AWARE>
 __device__ __forceinline__ bool hist_add_fast(unsigned int base_addr, unsigned int trash_addr, float v,
                                               const HistDiv &h)
 {
     const unsigned int bits = hist_fast_bits(v, h);
     const bool slow = hist_is_slow(bits);
-    const unsigned int addr = slow ? trash_addr : (((bits >> 10) & 0x1ffcu) | base_addr);
+    unsigned int addr = hist_fast_addr(bits, base_addr);
+    if (ZERO_AWARE) addr = slow ? trash_addr : addr;
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
     return ZERO_AWARE ? (slow && v != 0.0f) : slow;
 }
 
-// one thread's share of a full chunk part: VPT float4 -> bit i of the result flags float4 i
+// redo pass for one element of a flagged float4 (rare)
+template <bool ZERO_AWARE>
+__device__ __forceinline__ void hist_redo(unsigned int *sh, unsigned int base_addr, float v, const HistDiv &h)
+{
+    const unsigned int bits = hist_fast_bits(v, h);
+    if (!hist_is_slow(bits)) return;                       // was filed correctly by the hot loop
+    if (!ZERO_AWARE)                                       // take the provisional count back
+        asm volatile("red.shared.add.u32 [%0], -1;" ::"r"(hist_fast_addr(bits, base_addr)) : "memory");
+    hist_add_exact(sh, v, h.d);
+}
+
+// one thread's share of a chunk part: VPT float4 -> bit i of the result flags float4 i
 template <bool ZERO_AWARE, int VPT>
 __device__ __forceinline__ unsigned int hist_add_vecs(unsigned int base_addr, unsigned int trash_addr,
                                                       const float4 (&v)[VPT], const HistDiv &h)
@@ -194,6 +211,21 @@ __device__ __forceinline__ unsigned int hist_add_vecs(unsigned int base_addr, un
     return redo;
 }
 
+template <bool ZERO_AWARE>
+__device__ __forceinline__ void hist_redo_vecs(unsigned int redo, unsigned int *mine, unsigned int mine_addr,
+                                               const float4 *psrc, const HistDiv &h)
+{
+    while (redo) {                                         // rare: re-load the flagged float4s
+        const int slot = __ffs(redo) - 1;
+        redo &= redo - 1;
+        const float4 w = psrc[threadIdx.x + slot * kStatThreads];
+        hist_redo<ZERO_AWARE>(mine, mine_addr, w.x, h);
+        hist_redo<ZERO_AWARE>(mine, mine_addr, w.y, h);
+        hist_redo<ZERO_AWARE>(mine, mine_addr, w.z, h);
+        hist_redo<ZERO_AWARE>(mine, mine_addr, w.w, h);
+    }
+}
+
 constexpr size_t hist_smem_bytes(int copies) { return 8192 + (size_t)copies * PQ_HIST_BINS * 4 + 128; }
 
 template <int COPIES, int VPT = kVecPerThread>
@@ -202,7 +234,7 @@ hist_multi_kernel(const __grid_constant__ SegTable tab, unsigned long long *__re
 {
     // dynamic shared memory: hist_smem_bytes(COPIES)
     extern __shared__ unsigned int s_raw[];                // 8 KB alignment slack + [COPIES][2048] + trash
-    // align the histograms to 8 KB inside the shared window (see hist_add_fast)
+    // align the histograms to 8 KB inside the shared window (see hist_fast_addr)
     const unsigned int raw_addr = (unsigned int)__cvta_generic_to_shared(s_raw);
     const unsigned int pad = ((8192u - (raw_addr & 8191u)) & 8191u) >> 2;
     unsigned int *s_hist = s_raw + pad;
@@ -236,23 +268,15 @@ hist_multi_kernel(const __grid_constant__ SegTable tab, unsigned long long *__re
                     float4 v[VPT];
 #pragma unroll
                     for (int i = 0; i < VPT; ++i) v[i] = ld_stream_f4(psrc + threadIdx.x + i * kStatThreads);
-                    unsigned int redo;                      // bit i: float4 i holds a slow element
                     if (zero_aware) {
-                        redo = hist_add_vecs<true, VPT>(mine_addr, trash_addr, v, hd);
+                        const unsigned int redo = hist_add_vecs<true, VPT>(mine_addr, trash_addr, v, hd);
+                        hist_redo_vecs<true>(redo, mine, mine_addr, psrc, hd);
                     } else {
-                        redo = hist_add_vecs<false, VPT>(mine_addr, trash_addr, v, hd);
+                        const unsigned int redo = hist_add_vecs<false, VPT>(mine_addr, trash_addr, v, hd);
                         // a warp that keeps flagging (exact zeros in the data) switches, for the rest
                         // of its chunk range, to the variant that does not flag zeros
                         zero_aware = __any_sync(0xffffffffu, __popc(redo) >= 3);
-                    }
-                    while (redo) {                          // rare: re-load the flagged float4s
-                        const int slot = __ffs(redo) - 1;
-                        redo &= redo - 1;
-                        const float4 w = psrc[threadIdx.x + slot * kStatThreads];
-                        if (hist_is_slow(hist_fast_bits(w.x, hd))) hist_add_exact(mine, w.x, interval);
-                        if (hist_is_slow(hist_fast_bits(w.y, hd))) hist_add_exact(mine, w.y, interval);
-                        if (hist_is_slow(hist_fast_bits(w.z, hd))) hist_add_exact(mine, w.z, interval);
-                        if (hist_is_slow(hist_fast_bits(w.w, hd))) hist_add_exact(mine, w.w, interval);
+                        hist_redo_vecs<false>(redo, mine, mine_addr, psrc, hd);
                     }
                 }
             } else {
