@@ -185,9 +185,15 @@ def ours(args):
 
     # warm-up: W steps through the same job shape (cuDNN autotune, allocator, kernels)
     warm = [make_batch(10_000 + rank * W + i, device="cuda") for i in range(W)]
-    run_job(net, ShardedBatches(warm, W * world, rank, world), W * world, workdir, rank, world)
+    _, qw = run_job(net, ShardedBatches(warm, W * world, rank, world), W * world, workdir, rank, world)
     del warm
-    torch.cuda.empty_cache()
+    # Pre-size the caching allocator's pool for the K-batch activation cache so that no cudaMalloc
+    # lands inside the timed region: allocate one block of the expected size and release it to the pool.
+    per_batch = qw.timings["cached_bytes"] // max(1, qw.timings["cached_batches"])
+    free, _total = torch.cuda.mem_get_info()
+    want = min(int((K + 2) * per_batch * 1.05), int(free * 0.8))
+    if want > 0:
+        torch.empty(want, dtype=torch.uint8, device="cuda")
 
     # ---- value: inputs resident in HBM ---------------------------------------------------
     dev_batches = [make_batch(rank + world * i, device="cuda") for i in range(K)]
@@ -228,14 +234,14 @@ def ours(args):
                 "stats_share_of_step": round((hist["total_ms"] + amax["total_ms"]) / (secs * 1e3), 4)}
 
     # ---- e2e: host batches in pinned memory through the same public call ---------------------
-    torch.cuda.empty_cache()
     host_batches = [make_batch(rank + world * i, pin=True) for i in range(K)]
     e_secs, q2 = run_job(net, ShardedBatches(host_batches, K * world, rank, world), K * world, workdir, rank, world)
     n_fwd_pass2 = K - q2.timings.get("cached_batches", 0)
     h2d = (K + n_fwd_pass2) * MICRO_BATCH * int(np.prod(IMG_SHAPE)) * 4 / K
     d2h = (71 * 4 + 71 * 2048 * 8 + 71 * 4) / K
     e2e = {"value": round(world * K * MICRO_BATCH / e_secs, 2), "unit": UNIT,
-           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "phases_s": {k: round(v, 4) for k, v in q2.timings.items() if k.endswith("_s")}}
     assert q2.last_calibration["bits"]["image"] == bits_image
     del host_batches
 

@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Per-layer timing of the integer-simulation kernels on the 23 unique ResNet-50 conv geometries
+ at batch B: quantise (fp32 NCHW -> int8 NHWC) and conv (int8 -> fp32 NCHW).
+Prints a table; `--json` appends one JSON line.  Development tool, not the headline bench."""
+import argparse
+import json
+import os
+import sys
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "pytorch-quantity_b200"))
+import torch  # noqa: E402
+
+from common.quantity import _native  # noqa: E402
+
+# (Cin, H, W, Cout, k, stride, count)
+R50 = [(3, 224, 224, 64, 7, 2, 1), (64, 56, 56, 64, 1, 1, 1), (64, 56, 56, 64, 3, 1, 3), (64, 56, 56, 256, 1, 1, 4),
+       (256, 56, 56, 64, 1, 1, 2), (256, 56, 56, 128, 1, 1, 1), (128, 56, 56, 128, 3, 2, 1), (128, 28, 28, 512, 1, 1, 4),
+       (256, 56, 56, 512, 1, 2, 1), (512, 28, 28, 128, 1, 1, 3), (128, 28, 28, 128, 3, 1, 3), (512, 28, 28, 256, 1, 1, 1),
+       (256, 28, 28, 256, 3, 2, 1), (256, 14, 14, 1024, 1, 1, 6), (512, 28, 28, 1024, 1, 2, 1), (1024, 14, 14, 256, 1, 1, 5),
+       (256, 14, 14, 256, 3, 1, 5), (1024, 14, 14, 512, 1, 1, 1), (512, 14, 14, 512, 3, 2, 1), (512, 7, 7, 2048, 1, 1, 3),
+       (1024, 14, 14, 2048, 1, 2, 1), (2048, 7, 7, 512, 1, 1, 2), (512, 7, 7, 512, 3, 1, 2)]
+
+
+def time_ms(fn, iters=5):
+    for _ in range(2):
+        fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--s8-out", action="store_true", help="store int8 NHWC instead of fp32 NCHW")
+    args = ap.parse_args()
+    B = args.batch
+    tot_conv = tot_q = tot_ops = 0.0
+    print("%-28s %9s %8s %8s %8s %8s %8s" % ("layer (Cin,H,W,Cout,k,s)xN", "GOP", "conv_ms", "TOPS", "outGB/s", "quant_ms", "qGB/s"))
+    for (cin, h, w, cout, k, s, cnt) in R50:
+        pad = k // 2
+        plain = k == 1 and s == 1
+        cpad = (cin + 15) // 16 * 16 if plain else (cin + 31) // 32 * 32
+        x = torch.randn(B, cin, h, w, device="cuda")
+        wk = torch.randint(-128, 127, (cout, k, k, cpad), dtype=torch.int8, device="cuda")
+        wk[..., cin:] = 0
+        bias = torch.randint(-128, 127, (cout,), dtype=torch.int32, device="cuda")
+        P = (h + 2 * pad - k) // s + 1
+        if cin <= 8 and not plain:       # explicit im2col + GEMM (the stem)
+            kp = (k * k * cin + 63) // 64 * 64
+            wn = torch.randint(-128, 127, (cout, kp), dtype=torch.int8, device="cuda")
+            wn[:, k * k * cin:] = 0
+            q, _ = _native.quantize_im2col_s8(x, 4, (k, k), (s, s), (pad, pad), kp)
+            t_q = time_ms(lambda: _native.quantize_im2col_s8(x, 4, (k, k), (s, s), (pad, pad), kp))
+            t_c = time_ms(lambda: _native.gemm_s8(q, wn, bias, 9, 4, hw=P * P, want_f32=not args.s8_out,
+                                                  want_s8=args.s8_out))
+        else:
+            q = _native.quantize_nchw_to_nhwc_s8(x, 4, cpad)
+            t_q = time_ms(lambda: _native.quantize_nchw_to_nhwc_s8(x, 4, cpad))
+            t_c = time_ms(lambda: _native.conv2d_s8(q, wk, bias, (s, s), (pad, pad), 9, 4, want_f32=not args.s8_out,
+                                                    want_s8=args.s8_out))
+        ops = 2.0 * B * P * P * cout * k * k * cin
+        out_bytes = B * P * P * cout * (1 if args.s8_out else 4)
+        qbytes = x.numel() * 4 + q.numel()
+        print("%-28s %9.1f %8.3f %8.1f %8.0f %8.3f %8.0f" % ("(%d,%d,%d,%d,%d,%d)x%d" % (cin, h, w, cout, k, s, cnt), ops / 1e9,
+              t_c, ops / t_c / 1e9, out_bytes / t_c / 1e6, t_q, qbytes / t_q / 1e6))
+        tot_conv += t_c * cnt; tot_q += t_q * cnt; tot_ops += ops * cnt
+        del x, q, wk
+    print("TOTAL conv %.2f ms (%.1f TOPS), quantise %.2f ms, %.2f TOP" % (tot_conv, tot_ops / tot_conv / 1e9, tot_q, tot_ops / 1e12))
+    print(json.dumps({"batch": B, "conv_ms": round(tot_conv, 3), "quant_ms": round(tot_q, 3),
+                      "TOPS": round(tot_ops / tot_conv / 1e9, 1), "s8_out": args.s8_out}))
+
+
+if __name__ == "__main__":
+    main()

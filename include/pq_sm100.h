@@ -103,6 +103,14 @@ int pq_clamp_scale_f32(const float *x, float *y, size_t n, float lo, float hi, f
 int pq_quantize_nchw_to_nhwc_s8(const float *x, int8_t *q, int N, int C, int H, int W, int c_pad,
                                 int ib, pq_stream_t stream);
 
+/* ---- a12 for convolutions with very few input channels (the ResNet stem): Quantity.forward fused
+ * with an explicit im2col, a[m][k] = q(x[n][c][p*sh-ph+r][q*sw-pw+s]) for k = (r*S+s)*C + c, zero for
+ * padding and for k in [R*S*C, kp); m = (n*P + p)*Q + q, row pitch kp bytes (multiple of 16).  The
+ * result feeds pq_gemm_s8 with weights laid out [K][R][S][C] and zero-padded to kp. */
+int pq_quantize_im2col_s8(const float *x, int8_t *a, int N, int C, int H, int W, int R, int S,
+                          int stride_h, int stride_w, int pad_h, int pad_w, int kp, int ib,
+                          pq_stream_t stream);
+
 /* ---- a13 + a14: NewConv2d.forward / NewLinear.forward, new_quantity_op.py:104-133,177-205
  * (Conv -> RightShift -> BiasAdd -> Sp -> DeQuantity) on int8 operands:
  *   acc  = sum_k a[m][k] * w[n][k]                 int8 x int8 -> int32 (tcgen05 kind::i8)

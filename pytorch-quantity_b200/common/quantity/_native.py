@@ -33,6 +33,7 @@ SYMBOLS = {
     "pq_rshift_f32": (_i, [_vp, _vp, _sz, _i, _f, _f, _vp]),
     "pq_clamp_scale_f32": (_i, [_vp, _vp, _sz, _f, _f, _f, _vp]),
     "pq_quantize_nchw_to_nhwc_s8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "pq_quantize_im2col_s8": (_i, [_vp, _vp] + [_i] * 12 + [_vp]),
     "pq_gemm_s8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pq_conv2d_s8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
@@ -195,8 +196,9 @@ def add_clamp(a, b, lo=-128.0, hi=127.0):
         a, b = torch.broadcast_tensors(a, b)
     ac, y = _flat_out(a)
     bc = b.contiguous()
-    check(lib().pq_add_clamp_f32(ac.data_ptr(), bc.data_ptr(), y.data_ptr(), ac.numel(), lo, hi,
-                                 _stream(ac)), "pq_add_clamp_f32")
+    with _Timed("add_clamp", 1, 12 * ac.numel(), ac.device):
+        check(lib().pq_add_clamp_f32(ac.data_ptr(), bc.data_ptr(), y.data_ptr(), ac.numel(), lo, hi,
+                                     _stream(ac)), "pq_add_clamp_f32")
     return y
 
 
@@ -220,12 +222,30 @@ def quantize_nchw_to_nhwc_s8(x, ib, c_pad):
     xc = x.contiguous()
     N, C, H, W = xc.shape
     q = torch.empty((N, H, W, c_pad), dtype=torch.int8, device=x.device)
-    check(lib().pq_quantize_nchw_to_nhwc_s8(xc.data_ptr(), q.data_ptr(), N, C, H, W, c_pad, int(ib),
-                                            _stream(xc)), "pq_quantize_nchw_to_nhwc_s8")
+    with _Timed("quantize_s8", 1, xc.numel() * 4 + q.numel(), xc.device):
+        check(lib().pq_quantize_nchw_to_nhwc_s8(xc.data_ptr(), q.data_ptr(), N, C, H, W, c_pad, int(ib),
+                                                _stream(xc)), "pq_quantize_nchw_to_nhwc_s8")
     return q
 
 
-def gemm_s8(a, w, bias_q, rs, ob, hw=1, want_f32=True, want_s8=False):
+def quantize_im2col_s8(x, ib, kernel, stride, padding, kp):
+    """fp32 NCHW -> int8 [N*P*Q][kp] im2col matrix (small-Cin convolutions)."""
+    require_cuda(x, "quantize_im2col_s8")
+    assert x.dim() == 4 and x.dtype == torch.float32
+    xc = x.contiguous()
+    N, C, H, W = xc.shape
+    R, S = kernel
+    P = (H + 2 * padding[0] - R) // stride[0] + 1
+    Q = (W + 2 * padding[1] - S) // stride[1] + 1
+    a = torch.empty((N * P * Q, kp), dtype=torch.int8, device=x.device)
+    with _Timed("quantize_s8", 1, xc.numel() * 4 + a.numel(), xc.device):
+        check(lib().pq_quantize_im2col_s8(xc.data_ptr(), a.data_ptr(), N, C, H, W, R, S, stride[0], stride[1],
+                                          padding[0], padding[1], kp, int(ib), _stream(xc)),
+              "pq_quantize_im2col_s8")
+    return a, (N, P, Q)
+
+
+def gemm_s8(a, w, bias_q, rs, ob, hw=1, want_f32=True, want_s8=False, k_real=None):
     """a int8 [M][K], w int8 [N][K], bias_q int32 [N] -> fp32 (NCHW with hw pixels per image,
     or [M][N] when hw == 1) and / or int8 [M][N]."""
     require_cuda(a, "gemm_s8")
@@ -236,13 +256,14 @@ def gemm_s8(a, w, bias_q, rs, ob, hw=1, want_f32=True, want_s8=False):
         out_f32 = torch.empty((M // hw, N, hw) if hw > 1 else (M, N), dtype=torch.float32, device=a.device)
     if want_s8:
         out_s8 = torch.empty((M, N), dtype=torch.int8, device=a.device)
-    check(lib().pq_gemm_s8(a.data_ptr(), w.data_ptr(), bias_q.data_ptr(), M, N, K, int(rs), int(ob), hw,
-                           out_f32.data_ptr() if want_f32 else None,
-                           out_s8.data_ptr() if want_s8 else None, _stream(a)), "pq_gemm_s8")
+    with _Timed("gemm_s8", 1, 2 * M * N * (k_real or K), a.device):      # "bytes" field carries int8 ops here
+        check(lib().pq_gemm_s8(a.data_ptr(), w.data_ptr(), bias_q.data_ptr(), M, N, K, int(rs), int(ob), hw,
+                               out_f32.data_ptr() if want_f32 else None,
+                               out_s8.data_ptr() if want_s8 else None, _stream(a)), "pq_gemm_s8")
     return out_f32, out_s8
 
 
-def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, want_s8=False):
+def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, want_s8=False, c_real=None):
     require_cuda(x_nhwc, "conv2d_s8")
     N, H, W, C = x_nhwc.shape
     K, R, S, C2 = w_krsc.shape
@@ -252,7 +273,8 @@ def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, wa
     d = ConvDesc(N, H, W, C, K, R, S, stride[0], stride[1], padding[0], padding[1], P, Q, int(rs), int(ob))
     out_f32 = torch.empty((N, K, P, Q), dtype=torch.float32, device=x_nhwc.device) if want_f32 else None
     out_s8 = torch.empty((N, P, Q, K), dtype=torch.int8, device=x_nhwc.device) if want_s8 else None
-    check(lib().pq_conv2d_s8(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
-                             out_f32.data_ptr() if want_f32 else None,
-                             out_s8.data_ptr() if want_s8 else None, _stream(x_nhwc)), "pq_conv2d_s8")
+    with _Timed("conv_s8", 1, 2 * N * P * Q * K * R * S * (c_real or C), x_nhwc.device):   # int8 ops
+        check(lib().pq_conv2d_s8(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
+                                 out_f32.data_ptr() if want_f32 else None,
+                                 out_s8.data_ptr() if want_s8 else None, _stream(x_nhwc)), "pq_conv2d_s8")
     return out_f32, out_s8

@@ -159,6 +159,14 @@ class NewConv2d(_IntSimBase):
         K, C, R, S = wq.shape
         # im2col TMA fetches channel blocks of 32 / 64 / 128 bytes; a 1x1 stride-1 conv is a plain GEMM
         plain = (R, S) == (1, 1) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (0, 0)
+        # very few input channels (the ResNet stem): explicit im2col + GEMM instead of padding C to 32
+        self._explicit_im2col = (not plain) and C <= 8
+        if self._explicit_im2col:
+            self._k_pad = (R * S * C + 63) // 64 * 64
+            w_nk = torch.zeros((K, self._k_pad), dtype=torch.int8, device=wq.device)
+            w_nk[:, :R * S * C] = wq.permute(0, 2, 3, 1).reshape(K, -1).to(torch.int8)
+            self.register_buffer("_w_nk", w_nk.contiguous())
+            return
         self._c_pad = _pad16(C) if plain else _pad32(C)
         w_krsc = torch.zeros((K, R, S, self._c_pad), dtype=torch.int8, device=wq.device)
         w_krsc[..., :C] = wq.permute(0, 2, 3, 1).to(torch.int8)
@@ -166,9 +174,16 @@ class NewConv2d(_IntSimBase):
 
     def forward(self, input):
         conv = self.Conv
+        if self._explicit_im2col:
+            a, (N, P, Q) = _native.quantize_im2col_s8(input, self.input_bit, conv.kernel_size, conv.stride,
+                                                      conv.padding, self._k_pad)       # Quan + im2col
+            out, _ = _native.gemm_s8(a, self._w_nk, self._bias_i32, self.rs_bit, self.output_bit, hw=P * Q,
+                                     k_real=conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1])
+            return out.view(N, conv.out_channels, P, Q)
         q = _native.quantize_nchw_to_nhwc_s8(input, self.input_bit, self._c_pad)        # Quan
         out, _ = _native.conv2d_s8(q, self._w_krsc, self._bias_i32, conv.stride, conv.padding,
-                                   self.rs_bit, self.output_bit)  # Conv+RightShift+BiasAdd+Sp+DeQuan
+                                   self.rs_bit, self.output_bit,
+                                   c_real=conv.in_channels)      # Conv+RightShift+BiasAdd+Sp+DeQuan
         return out
 
 
@@ -195,7 +210,8 @@ class NewLinear(_IntSimBase):
         # Quan: a [B][K] matrix is NCHW with H = W = 1, so the same kernel quantises and pads it
         q = _native.quantize_nchw_to_nhwc_s8(x2.view(x2.shape[0], x2.shape[1], 1, 1), self.input_bit,
                                              self._k_pad).view(x2.shape[0], self._k_pad)
-        out, _ = _native.gemm_s8(q, self._w_nk, self._bias_i32, self.rs_bit, self.output_bit)
+        out, _ = _native.gemm_s8(q, self._w_nk, self._bias_i32, self.rs_bit, self.output_bit,
+                                 k_real=self.Linear.in_features)
         return out.view(*input.shape[:-1], out.shape[-1])
 
 
@@ -250,7 +266,7 @@ def _dump_diagnostics(path, name, tag, before, after):
 class _FakeQuantBase(nn.Module):
     def _setup(self, name, module, quantize_infor, new_model_path, out_features):
         self.name = name
-        self.path = os.path.join(os.path.dirname(new_model_path), "quantity_results")
+        self.path = os.path.join(os.path.dirname(new_model_path or "."), "quantity_results")
         if WRITE_DIAGNOSTICS and not os.path.exists(self.path):
             os.makedirs(self.path)
         self.weight_bit = quantize_infor["weight_bit"]

@@ -126,9 +126,8 @@ unary_kernel(const float *__restrict__ x, float *__restrict__ y, size_t n, float
     }
 }
 
-// NCHW fp32 -> NHWC int8 with channel padding.  One CTA transposes a [32 channels][32 pixels]
-// tile through shared memory: coalesced 128 B fp32 reads along pixels, 32 B int8 writes per
-// pixel row along channels (c_pad is a multiple of 16, so rows are 16-byte aligned).
+// NCHW fp32 -> NHWC int8 with channel padding (generic path: any H*W, scalar loads).  One CTA
+// transposes a [32 channels][32 pixels] tile through shared memory.
 __global__ void __launch_bounds__(256)
 quantize_nchw_nhwc_kernel(const float *__restrict__ x, int8_t *__restrict__ q, int C, int HW,
                           int c_pad, float scale)
@@ -152,6 +151,106 @@ quantize_nchw_nhwc_kernel(const float *__restrict__ x, int8_t *__restrict__ q, i
     for (int j = 0; j < 4; ++j) {
         const int p = p0 + ty + j * 8, c = c0 + tx;
         if (p < HW && c < c_pad) dst[(size_t)p * c_pad + c] = tile[tx][ty + j * 8];
+    }
+}
+
+// Fast path (H*W % 4 == 0, 16-byte aligned rows): one CTA converts [32 channels][128 pixels].
+// Each warp streams 4 channel rows with 512-byte coalesced LDG.128s (16 values per thread in
+// flight), quantises, packs its 4 consecutive channels of one pixel into one 32-bit word and
+// stores it to a [128 pixels][32 channels] shared tile; the tile leaves as 16-byte vectors, one
+// full 32-byte sector per pixel row.
+__device__ __forceinline__ unsigned int q8(float v, float scale)
+{
+    return (unsigned int)(int)clamp_nan(rintf(__fmul_rn(v, scale)), -128.0f, 127.0f) & 0xffu;
+}
+
+__global__ void __launch_bounds__(256)
+quantize_nchw_nhwc_vec_kernel(const float *__restrict__ x, int8_t *__restrict__ q, int C, int HW,
+                              int c_pad, float scale)
+{
+    __shared__ __align__(16) unsigned int tile[128][8 + 1];     // 128 pixels x 32 channel bytes (+pad)
+    const int n = blockIdx.z;
+    const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float *src = x + ((size_t)n * C + c0 + warp * 4) * HW + p0 + lane * 4;
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + warp * 4 + j;
+        v[j] = (c < C && p0 + lane * 4 < HW) ? ld_stream_f4(reinterpret_cast<const float4 *>(src + (size_t)j * HW))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    tile[lane * 4 + 0][warp] = q8(v[0].x, scale) | (q8(v[1].x, scale) << 8) | (q8(v[2].x, scale) << 16) | (q8(v[3].x, scale) << 24);
+    tile[lane * 4 + 1][warp] = q8(v[0].y, scale) | (q8(v[1].y, scale) << 8) | (q8(v[2].y, scale) << 16) | (q8(v[3].y, scale) << 24);
+    tile[lane * 4 + 2][warp] = q8(v[0].z, scale) | (q8(v[1].z, scale) << 8) | (q8(v[2].z, scale) << 16) | (q8(v[3].z, scale) << 24);
+    tile[lane * 4 + 3][warp] = q8(v[0].w, scale) | (q8(v[1].w, scale) << 8) | (q8(v[2].w, scale) << 16) | (q8(v[3].w, scale) << 24);
+    __syncthreads();
+    // 128 pixels x 32 bytes = 256 x 16 bytes: thread t writes half a pixel row
+    const int p = threadIdx.x >> 1, half = threadIdx.x & 1;
+    if (p0 + p < HW && c0 + half * 16 < c_pad) {
+        const uint4 w = make_uint4(tile[p][half * 4 + 0], tile[p][half * 4 + 1], tile[p][half * 4 + 2], tile[p][half * 4 + 3]);
+        *reinterpret_cast<uint4 *>(q + ((size_t)n * HW + p0 + p) * c_pad + c0 + half * 16) = w;
+    }
+}
+
+// Fused input quantiser + explicit im2col for convolutions with very few input channels (the
+// ResNet stem, Cin = 3): writes A[m][k] = q(x[n][c][p*sh-ph+r][q*sw-pw+s]) for k = (r*S+s)*C + c,
+// zero for padding and for k >= R*S*C (row pitch kp, a multiple of 16).  Padding the channels to
+// the 32-byte granularity of the im2col TMA instead would multiply the GEMM K by 10.
+// Each warp owns 32 consecutive output pixels: for every k the 32 lanes gather one fp32 each from
+// neighbouring input columns (coalesced, L1/L2 hits: every input value is used R*S/(sh*sw) times),
+// quantise, and pack four k into a word of a [32 pixels][kp bytes] shared tile (odd word pitch, no
+// bank conflicts); the tile -- 32 contiguous rows of A -- then leaves with 128-byte coalesced stores.
+constexpr int kIm2colWarps = 8;
+
+// round-half-even + saturate in two instructions (F2I.RN saturates, then an integer clamp)
+__device__ __forceinline__ int q8i(float v, float scale)
+{
+    return max(-128, min(127, __float2int_rn(__fmul_rn(v, scale))));
+}
+
+__global__ void __launch_bounds__(kIm2colWarps * 32)
+quantize_im2col_kernel(const float *__restrict__ x, int8_t *__restrict__ a, int C, int H, int W, int R, int S,
+                       int sh, int sw, int ph, int pw, int P, int Q, int kp, long long M, float scale)
+{
+    extern __shared__ unsigned int s_mem[];
+    const int kw = kp >> 2;                         // words per row
+    const int pitch = kw | 1;                       // odd word pitch: conflict-free column access
+    unsigned int *s_tile = s_mem + (threadIdx.x >> 5) * 32 * pitch;
+    const int lane = threadIdx.x & 31;
+    const int HWi = H * W;
+    const long long warps_total = (M + 31) / 32;
+    for (long long wi = (long long)blockIdx.x * kIm2colWarps + (threadIdx.x >> 5); wi < warps_total;
+         wi += (long long)gridDim.x * kIm2colWarps) {
+        const long long m = wi * 32 + lane;
+        const bool live = m < M;
+        const int qx = (int)(m % Q);
+        const long long mp = m / Q;
+        const int py = (int)(mp % P);
+        const long long n = mp / P;
+        const float *img = x + n * (long long)C * HWi;
+        const int iy0 = py * sh - ph, ix0 = qx * sw - pw;
+        int8_t *row = reinterpret_cast<int8_t *>(s_tile + lane * pitch);
+        int k = 0;
+        for (int r = 0; r < R; ++r) {
+            const int iy = iy0 + r;
+            const bool rok = live && (unsigned)iy < (unsigned)H;
+            for (int s_ = 0; s_ < S; ++s_) {
+                const int ix = ix0 + s_;
+                const bool ok = rok && (unsigned)ix < (unsigned)W;
+                const float *src = img + iy * W + ix;
+                for (int c = 0; c < C; ++c, ++k)
+                    row[k] = (int8_t)(ok ? q8i(__ldg(src + c * HWi), scale) : 0);
+            }
+        }
+        for (; k < kp; ++k) row[k] = 0;             // K padding
+        __syncwarp();
+        // 32 rows x kw words are contiguous in A: coalesced word stores
+        unsigned int *dst = reinterpret_cast<unsigned int *>(a + wi * 32 * (long long)kp);
+        const long long words_live = (M - wi * 32 < 32 ? M - wi * 32 : 32) * kw;
+        for (int w = lane; w < 32 * kw; w += 32)
+            if (w < words_live) dst[w] = s_tile[(w / kw) * pitch + (w % kw)];
+        __syncwarp();
     }
 }
 
@@ -225,8 +324,40 @@ extern "C" int pq_quantize_nchw_to_nhwc_s8(const float *x, int8_t *q, int N, int
     if (c_pad < C || (c_pad & 15)) return PQ_EUNSUPPORTED;
     if (ib < -126 || ib > 126 || N > 65535) return PQ_EUNSUPPORTED;
     const int HW = H * W;
-    dim3 grid((HW + 31) / 32, (c_pad + 31) / 32, N);
-    if (grid.y > 65535) return PQ_EUNSUPPORTED;
-    pq::quantize_nchw_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, q, C, HW, c_pad, ldexpf(1.0f, ib));
+    if ((c_pad + 31) / 32 > 65535) return PQ_EUNSUPPORTED;
+    if ((HW & 3) == 0 && aligned16(x) && aligned16(q)) {
+        dim3 grid((HW + 127) / 128, (c_pad + 31) / 32, N);
+        pq::quantize_nchw_nhwc_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, q, C, HW, c_pad, ldexpf(1.0f, ib));
+    } else {
+        dim3 grid((HW + 31) / 32, (c_pad + 31) / 32, N);
+        pq::quantize_nchw_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, q, C, HW, c_pad, ldexpf(1.0f, ib));
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pq_quantize_im2col_s8(const float *x, int8_t *a, int N, int C, int H, int W, int R, int S,
+                                     int stride_h, int stride_w, int pad_h, int pad_w, int kp, int ib,
+                                     pq_stream_t stream)
+{
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || R <= 0 || S <= 0 || stride_h <= 0 || stride_w <= 0) return PQ_EINVAL;
+    if (!x || !a || pad_h < 0 || pad_w < 0) return PQ_EINVAL;
+    if (kp < R * S * C || (kp & 15) || ib < -126 || ib > 126) return PQ_EUNSUPPORTED;
+    if (!aligned16(a)) return PQ_EALIGN;
+    const int P = (H + 2 * pad_h - R) / stride_h + 1, Q = (W + 2 * pad_w - S) / stride_w + 1;
+    if (P <= 0 || Q <= 0) return PQ_EINVAL;
+    const long long M = (long long)N * P * Q;
+    const size_t smem = (size_t)(pq::kIm2colWarps * 32 * ((kp >> 2) | 1)) * sizeof(unsigned int);
+    if (smem > 200 * 1024) return PQ_EUNSUPPORTED;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        PQ_CUDA_TRY(cudaFuncSetAttribute(pq::quantize_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        attr_smem = smem;
+    }
+    const long long warps = (M + 31) / 32;
+    long long blocks = (warps + pq::kIm2colWarps - 1) / pq::kIm2colWarps;
+    if (blocks > pq::kNumSMs * 8) blocks = pq::kNumSMs * 8;
+    pq::quantize_im2col_kernel<<<(unsigned int)blocks, pq::kIm2colWarps * 32, smem, (cudaStream_t)stream>>>(
+        x, a, C, H, W, R, S, stride_h, stride_w, pad_h, pad_w, P, Q, kp, M, ldexpf(1.0f, ib));
     return (int)cudaGetLastError();
 }

@@ -4,17 +4,21 @@
 //   RightShift -> BiasAdd -> Sp -> DeQuantity        (new_quantity_op.py:11-44, 61-101, 124-133)
 // chain fused into the epilogue.
 //
-// One CTA computes one 128 x BN output tile:
+// Persistent kernel, one CTA per SM, looping over 128 x BN output tiles (n fastest, so consecutive
+// tiles reuse the same activation rows out of L2):
 //   warp 0   : TMA producer.  A tile = 128 output pixels x BK input channels of ONE filter tap,
 //              fetched by a single im2col-mode TMA (padding = hardware zero fill, stride =
 //              traversal stride), or a plain 2-D tile for GEMMs / 1x1 stride-1 convolutions.
 //              B tile = BN filters x the same BK-byte slice of the [K][R*S*C] weight matrix.
-//   warp 1   : allocates TMEM, issues tcgen05.mma (one elected lane), commits to mbarriers.
-//   warps 2-5: epilogue.  tcgen05.ld the int32 accumulators (lane = output pixel, column = output
-//              channel), shift / round-half-away / saturate, + bias, saturate, then either
-//              de-quantise to fp32 NCHW (the module boundary of the reference) or store int8 NHWC.
-// A STAGES-deep mbarrier ring decouples the three roles; two CTAs fit per SM so one tile's
-// epilogue overlaps the other's main loop.
+//   warp 1   : allocates TMEM (two accumulators of BN columns), issues tcgen05.mma (one elected
+//              lane), commits to mbarriers.
+//   warps 2-17: epilogue, four warps per TMEM lane quadrant, each taking a quarter of the columns,
+//              TMEM loads software-pipelined against the arithmetic and the stores:
+//              tcgen05.ld the int32 accumulators (lane = output pixel, column = output channel),
+//              shift / round-half-away / saturate, + bias, saturate, then de-quantise to fp32 NCHW
+//              (the module boundary of the reference) and / or store int8 NHWC.
+// A STAGES-deep smem ring (full/empty mbarriers) decouples TMA from MMA; the two TMEM accumulators
+// (tmem_full/tmem_empty mbarriers) let the epilogue of tile i overlap the main loop of tile i+1.
 #include <cuda.h>
 
 #include "pq_common.cuh"
@@ -22,7 +26,8 @@
 namespace pq {
 
 constexpr int kBM = 128;               // UMMA M (cta_group::1): one TMEM lane per output row
-constexpr int kGemmThreads = 192;      // 6 warps: TMA, MMA, 4 x epilogue
+constexpr int kEpiWarps = 16;           // four per TMEM lane quadrant
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // TMA warp, MMA warp, epilogue warps
 
 // ------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -35,6 +40,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -111,8 +120,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory operand descriptor (cute::UMMA::SmemDescriptor): rows of BK bytes, swizzle
 // span == BK, 8-row groups SBO = 8*BK bytes apart; version 1 (Blackwell).
@@ -150,19 +166,28 @@ struct GemmParams {
     int8_t *out_s8;            // optional, [M][N]
 };
 
-// RightShift (round half away from zero, saturate) + BiasAdd + Sp, all in integers.
-__device__ __forceinline__ int requant(int acc, int rs, int bias)
+// RightShift (round half away from zero, saturate) + BiasAdd + Sp, all in integers, branch-free:
+//   rs >= 1:  round_half_away(acc / 2^rs) = (acc + 2^(rs-1) - (acc < 0)) >> rs   (arithmetic shift)
+//   rs <= 0:  acc * 2^-rs, saturated first (the shift is monotone)
+struct Requant {
+    int half, sh, mul;         // rs >= 1: half = 2^(rs-1), sh = rs, mul unused; rs <= 0: mul = 2^-rs
+    bool pos;
+};
+__device__ __forceinline__ Requant make_requant(int rs)
+{
+    Requant q;
+    q.pos = rs >= 1;
+    q.half = rs >= 1 ? (1 << (rs - 1)) : 0;
+    q.sh = rs >= 1 ? rs : 0;
+    q.mul = rs >= 1 ? 1 : (1 << (-rs));
+    return q;
+}
+__device__ __forceinline__ int requant(int acc, const Requant &q, int bias)
 {
     int r;
-    if (rs >= 1) {
-        const int a = acc < 0 ? -acc : acc;
-        const int mag = rs > 30 ? 0 : (int)(((unsigned int)a + (1u << (rs - 1))) >> rs);
-        r = acc < 0 ? -mag : mag;
-        r = max(-128, min(127, r));
-    } else {
-        r = max(-128, min(127, acc));                 // saturate first: the left shift is monotone
-        r = max(-128, min(127, r * (1 << (-rs > 8 ? 8 : -rs))));
-    }
+    if (q.pos) r = (acc + q.half + (acc >> 31)) >> q.sh;
+    else r = max(-128, min(127, acc)) * q.mul;
+    r = max(-128, min(127, r));
     return max(-128, min(127, r + bias));
 }
 
@@ -175,7 +200,7 @@ struct GemmSmem {
 };
 
 template <int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p)
 {
@@ -186,18 +211,20 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t *smem_b = smem + (size_t)STAGES * Cfg::kABytes;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * Cfg::kStageBytes);
     uint64_t *empty_bar = full_bar + STAGES;
-    uint64_t *tmem_full_bar = empty_bar + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+    uint64_t *tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
-    constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+    constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int total_tiles = ((p.M + kBM - 1) / kBM) * n_tiles;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -209,31 +236,34 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int wq = 0, hp = 0, nb = 0;
-            if (p.a_im2col) {                          // first output pixel of the tile -> input coords
-                const int pq = p.P * p.Q;
-                nb = m0 / pq;
-                const int rem = m0 - nb * pq;
-                hp = rem / p.Q;
-                wq = rem - hp * p.Q;
-            }
             int stage = 0; uint32_t phase = 0;
-            int r = 0, s = 0, cb = 0;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                mbar_wait(empty_bar + stage, phase ^ 1);
-                mbar_expect_tx(full_bar + stage, Cfg::kStageBytes);
-                void *dst_a = smem_a + (size_t)stage * Cfg::kABytes;
-                void *dst_b = smem_b + (size_t)stage * Cfg::kBBytes;
-                if (p.a_im2col) {
-                    tma_load_im2col_4d(&tmap_a, full_bar + stage, dst_a, cb * BK, wq * p.stride_w - p.pad_w,
-                                       hp * p.stride_h - p.pad_h, nb, (uint16_t)s, (uint16_t)r);
-                    tma_load_2d(&tmap_b, full_bar + stage, dst_b, (r * p.S + s) * p.C + cb * BK, n0);
-                    if (++cb == p.cblocks) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
-                } else {
-                    tma_load_2d(&tmap_a, full_bar + stage, dst_a, kb * BK, m0);
-                    tma_load_2d(&tmap_b, full_bar + stage, dst_b, kb * BK, n0);
+            const int pq = p.P * p.Q;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+                int wq = 0, hp = 0, nb = 0;
+                if (p.a_im2col) {                      // first output pixel of the tile -> input coords
+                    nb = m0 / pq;
+                    const int rem = m0 - nb * pq;
+                    hp = rem / p.Q;
+                    wq = rem - hp * p.Q;
                 }
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                int r = 0, s = 0, cb = 0;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    mbar_expect_tx(full_bar + stage, Cfg::kStageBytes);
+                    void *dst_a = smem_a + (size_t)stage * Cfg::kABytes;
+                    void *dst_b = smem_b + (size_t)stage * Cfg::kBBytes;
+                    if (p.a_im2col) {
+                        tma_load_im2col_4d(&tmap_a, full_bar + stage, dst_a, cb * BK, wq * p.stride_w - p.pad_w,
+                                           hp * p.stride_h - p.pad_h, nb, (uint16_t)s, (uint16_t)r);
+                        tma_load_2d(&tmap_b, full_bar + stage, dst_b, (r * p.S + s) * p.C + cb * BK, n0);
+                        if (++cb == p.cblocks) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
+                    } else {
+                        tma_load_2d(&tmap_a, full_bar + stage, dst_a, kb * BK, m0);
+                        tma_load_2d(&tmap_b, full_bar + stage, dst_b, kb * BK, n0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -241,70 +271,129 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_i8(kBM, BN < 16 ? 16 : BN);
             int stage = 0; uint32_t phase = 0;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                mbar_wait(full_bar + stage, phase);
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint64_t da = make_smem_desc<BK>(smem_u32(smem_a + (size_t)stage * Cfg::kABytes));
-                const uint64_t db = make_smem_desc<BK>(smem_u32(smem_b + (size_t)stage * Cfg::kBBytes));
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc<BK>(smem_u32(smem_a + (size_t)stage * Cfg::kABytes));
+                    const uint64_t db = make_smem_desc<BK>(smem_u32(smem_b + (size_t)stage * Cfg::kBBytes));
 #pragma unroll
-                for (int k = 0; k < BK / 32; ++k)      // UMMA_K = 32 int8: advance 32 B inside the swizzle span
-                    umma_i8(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                umma_commit(empty_bar + stage);        // frees the smem slot when these MMAs retire
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    for (int k = 0; k < BK / 32; ++k)  // UMMA_K = 32 int8: advance 32 B inside the swizzle span
+                        umma_i8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    umma_commit(empty_bar + stage);    // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tmem_full_bar + acc);      // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            umma_commit(tmem_full_bar);                // accumulator complete
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..17) =====================
         const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+        const int part = (warp - 2) >> 2;              // which quarter of the tile's columns
+        constexpr int kCols = BN / 4;                  // columns per epilogue warp: 8, 16, 32 or 64
+        constexpr int kChunk = kCols < 16 ? kCols : 16;
+        constexpr int kChunks = kCols / kChunk;
         const int row = quad * 32 + lane;
-        const int m = m0 + row;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
+        const Requant rq = make_requant(p.rs);
         const float dq = __int_as_float((127 - p.ob) << 23);        // 2^-ob, exact
-        long long img = 0; int pix = 0;
-        if (p.hw > 1) { img = m / p.hw; pix = m - (int)img * p.hw; }
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            if (n0 + c0 >= p.N) break;
-            uint32_t acc[16];
-            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, acc);
-            if (m < p.M) {
-                int y[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + c0 + j;
-                    y[j] = requant((int)acc[j], p.rs, n < p.N ? __ldg(p.bias + n) : 0);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN + part * kCols;
+            const int m = m0 + row;
+            float *of = nullptr;
+            size_t cstride = 1;
+            if (p.out_f32) {
+                if (p.hw > 1) {                        // NCHW: lanes of a warp write consecutive pixels
+                    const int img = m / p.hw, pix = m - img * p.hw;
+                    of = p.out_f32 + ((size_t)img * p.N + n0) * p.hw + pix;
+                    cstride = (size_t)p.hw;
+                } else {
+                    of = p.out_f32 + (size_t)m * p.N + n0;
                 }
-                if (p.out_f32) {
-                    if (p.hw > 1) {                    // NCHW: lanes of a warp write consecutive pixels
-                        float *o = p.out_f32 + ((size_t)img * p.N + n0 + c0) * p.hw + pix;
+            }
+            int8_t *o8 = p.out_s8 ? p.out_s8 + (size_t)m * p.N + n0 : nullptr;
+            mbar_wait(tmem_full_bar + acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kCols);
+
+            // process one chunk of kChunk columns held in registers
+            auto emit = [&](const uint32_t (&a)[16], int c0) {
+                if (!(m < p.M && n0 + c0 < p.N)) return;
+                int y[16];
+                const bool full = n0 + c0 + kChunk <= p.N;
+                if (full && kChunk == 16) {            // bias is 64-byte aligned here: 4 x LDG.128, warp-uniform
+                    const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + c0 + j < p.N) o[(size_t)j * p.hw] = __fmul_rn((float)y[j], dq);
+                    for (int j = 0; j < 4; ++j) {
+                        const int4 b4 = __ldg(bp + j);
+                        y[4 * j] = requant((int)a[4 * j], rq, b4.x); y[4 * j + 1] = requant((int)a[4 * j + 1], rq, b4.y);
+                        y[4 * j + 2] = requant((int)a[4 * j + 2], rq, b4.z); y[4 * j + 3] = requant((int)a[4 * j + 3], rq, b4.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j)
+                        y[j] = requant((int)a[j], rq, n0 + c0 + j < p.N ? __ldg(p.bias + n0 + c0 + j) : 0);
+                }
+                if (of) {
+                    if (p.hw > 1) {
+#pragma unroll
+                        for (int j = 0; j < kChunk; ++j)
+                            if (full || n0 + c0 + j < p.N) of[(size_t)(c0 + j) * cstride] = __fmul_rn((float)y[j], dq);
+                    } else if (full && (p.N & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < kChunk / 4; ++j)
+                            *reinterpret_cast<float4 *>(of + c0 + 4 * j) =
+                                make_float4(__fmul_rn((float)y[4 * j], dq), __fmul_rn((float)y[4 * j + 1], dq),
+                                            __fmul_rn((float)y[4 * j + 2], dq), __fmul_rn((float)y[4 * j + 3], dq));
                     } else {
-                        float *o = p.out_f32 + (size_t)m * p.N + n0 + c0;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + c0 + j < p.N) o[j] = __fmul_rn((float)y[j], dq);
+                        for (int j = 0; j < kChunk; ++j)
+                            if (full || n0 + c0 + j < p.N) of[c0 + j] = __fmul_rn((float)y[j], dq);
                     }
                 }
-                if (p.out_s8) {
-                    int8_t *o = p.out_s8 + (size_t)m * p.N + n0 + c0;
-                    if (n0 + c0 + 16 <= p.N && (p.N & 15) == 0) {
+                if (o8) {
+                    if (full && kChunk == 16 && (p.N & 15) == 0) {
                         uint32_t w[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             w[j] = (uint32_t)(y[4 * j] & 0xff) | ((uint32_t)(y[4 * j + 1] & 0xff) << 8) |
                                    ((uint32_t)(y[4 * j + 2] & 0xff) << 16) | ((uint32_t)(y[4 * j + 3] & 0xff) << 24);
-                        *reinterpret_cast<uint4 *>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4 *>(o8 + c0) = make_uint4(w[0], w[1], w[2], w[3]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + c0 + j < p.N) o[j] = (int8_t)y[j];
+                        for (int j = 0; j < kChunk; ++j)
+                            if (full || n0 + c0 + j < p.N) o8[c0 + j] = (int8_t)y[j];
                     }
                 }
+            };
+            auto load = [&](uint32_t (&a)[16], int c0) {
+                if (kChunk == 16) tmem_ld16(taddr + (uint32_t)c0, a); else tmem_ld8(taddr + (uint32_t)c0, a);
+            };
+
+            // software pipeline: the TMEM load of chunk i+1 is in flight while chunk i is processed
+            uint32_t a0[16], a1[16];
+            load(a0, 0);
+#pragma unroll
+            for (int ch = 0; ch < kChunks; ch += 2) {
+                tmem_ld_wait();
+                if (ch + 1 < kChunks) load(a1, (ch + 1) * kChunk);
+                emit(a0, ch * kChunk);
+                if (ch + 1 < kChunks) {
+                    tmem_ld_wait();
+                    if (ch + 2 < kChunks) load(a0, (ch + 2) * kChunk);
+                    emit(a1, (ch + 1) * kChunk);
+                }
             }
+            // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -381,34 +470,57 @@ int encode_im2col(CUtensorMap *map, const void *base, const pq_conv_desc &d, int
     return PQ_OK;
 }
 
+int num_sms()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = pq::kNumSMs;
+    }
+    return n;
+}
+
 template <int BN, int BK, int STAGES>
 int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, const pq::GemmParams &p, cudaStream_t s)
 {
     using Cfg = pq::GemmSmem<BN, BK, STAGES>;
+    static_assert(Cfg::kTotal <= 227 * 1024, "shared memory budget");
     auto kern = pq::gemm_s8_kernel<BN, BK, STAGES>;
     static bool attr = false;
     if (!attr) {
         PQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kTotal));
         attr = true;
     }
-    dim3 grid((p.M + pq::kBM - 1) / pq::kBM, (p.N + BN - 1) / BN);
+    const long long tiles = (long long)((p.M + pq::kBM - 1) / pq::kBM) * ((p.N + BN - 1) / BN);
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());     // persistent: one CTA per SM
     kern<<<grid, pq::kGemmThreads, Cfg::kTotal, s>>>(ta, tb, p);
     return (int)cudaGetLastError();
 }
 
+// stage counts: fill ~192 KB of shared memory, at most 8 stages
 template <int BK>
 int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, const pq::GemmParams &p, int bn, cudaStream_t s)
 {
-    constexpr int S128 = BK == 128 ? 3 : (BK == 64 ? 6 : 8);
-    constexpr int S64 = BK == 128 ? 4 : 8;
+    constexpr int S256 = BK == 128 ? 4 : 8;
+    constexpr int S128 = BK == 128 ? 6 : 8;
     switch (bn) {
+        case 256: return launch_cfg<256, BK, S256>(ta, tb, p, s);
         case 128: return launch_cfg<128, BK, S128>(ta, tb, p, s);
-        case 64: return launch_cfg<64, BK, S64>(ta, tb, p, s);
+        case 64: return launch_cfg<64, BK, 8>(ta, tb, p, s);
         default: return launch_cfg<32, BK, 8>(ta, tb, p, s);
     }
 }
 
-int pick_bn(int n) { return n > 64 ? 128 : (n > 32 ? 64 : 32); }
+// widest tile that still leaves every SM at least two tiles; never wider than N needs
+int pick_bn(long long m, int n)
+{
+    const long long m_tiles = (m + pq::kBM - 1) / pq::kBM;
+    const int cap = n > 128 ? 256 : (n > 64 ? 128 : (n > 32 ? 64 : 32));
+    for (int bn = cap; bn > 32; bn >>= 1)
+        if (m_tiles * ((n + bn - 1) / bn) >= 2LL * num_sms()) return bn;
+    return 32 < cap && m_tiles * ((n + 63) / 64) >= num_sms() ? 64 : 32;
+}
 
 int launch(const CUtensorMap &ta, const CUtensorMap &tb, const pq::GemmParams &p, int bk, int bn, cudaStream_t s)
 {
@@ -427,11 +539,12 @@ extern "C" int pq_gemm_s8(const int8_t *a, const int8_t *w, const int32_t *bias_
     if (M <= 0 || N <= 0 || K <= 0 || hw <= 0) return PQ_EINVAL;
     if (!a || !w || !bias_q || (!out_f32 && !out_s8)) return PQ_EINVAL;
     if ((K & 15) || (((uintptr_t)a | (uintptr_t)w) & 15)) return PQ_EALIGN;
-    if (ob < -100 || ob > 100 || (hw > 1 && M % hw)) return PQ_EUNSUPPORTED;
+    if (ob < -100 || ob > 100 || rs > 24 || rs < -24 || (hw > 1 && M % hw)) return PQ_EUNSUPPORTED;
+    if ((uintptr_t)bias_q & 15) return PQ_EALIGN;
     int rc = load_driver_entry_points();
     if (rc != PQ_OK) return rc;
     const int bk = K >= 128 ? 128 : (K >= 64 ? 64 : 32);
-    const int bn = pick_bn(N);
+    const int bn = pick_bn(M, N);
     CUtensorMap ta, tb;
     if ((rc = encode_2d(&ta, a, K, M, K, bk, pq::kBM)) != PQ_OK) return rc;
     if ((rc = encode_2d(&tb, w, K, N, K, bk, bn)) != PQ_OK) return rc;
@@ -452,7 +565,8 @@ extern "C" int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const in
     if (d.P != (d.H + 2 * d.pad_h - d.R) / d.stride_h + 1 || d.Q != (d.W + 2 * d.pad_w - d.S) / d.stride_w + 1)
         return PQ_EINVAL;
     if ((d.C & 15) || (((uintptr_t)x_nhwc | (uintptr_t)w_krsc) & 15)) return PQ_EALIGN;
-    if (d.ob < -100 || d.ob > 100 || d.stride_h > 8 || d.stride_w > 8) return PQ_EUNSUPPORTED;
+    if (d.ob < -100 || d.ob > 100 || d.rs > 24 || d.rs < -24 || d.stride_h > 8 || d.stride_w > 8) return PQ_EUNSUPPORTED;
+    if ((uintptr_t)bias_q & 15) return PQ_EALIGN;
     const long long M = (long long)d.N * d.P * d.Q;
     if (M > 0x7fffffffLL) return PQ_EUNSUPPORTED;
     if (d.R == 1 && d.S == 1 && d.stride_h == 1 && d.stride_w == 1 && d.pad_h == 0 && d.pad_w == 0)
@@ -462,7 +576,7 @@ extern "C" int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const in
     int rc = load_driver_entry_points();
     if (rc != PQ_OK) return rc;
     const int bk = (d.C % 128 == 0) ? 128 : ((d.C % 64 == 0) ? 64 : 32);
-    const int bn = pick_bn(d.K);
+    const int bn = pick_bn(M, d.K);
     CUtensorMap ta, tb;
     if ((rc = encode_im2col(&ta, x_nhwc, d, bk)) != PQ_OK) return rc;
     const uint64_t ktot = (uint64_t)d.R * d.S * d.C;

@@ -247,7 +247,9 @@ class Quantity(object):
         budget = self.cache_bytes
         if budget is None:
             free, _total = torch.cuda.mem_get_info(self.cuda_device)
-            budget = int(free * 0.6)
+            # memory the caching allocator already holds but is not using is just as available
+            pooled = torch.cuda.memory_reserved(self.cuda_device) - torch.cuda.memory_allocated(self.cuda_device)
+            budget = int((free + pooled) * 0.6)
         cache, cached_bytes, n_cached = {}, 0, 0
 
         t0 = time.perf_counter()
