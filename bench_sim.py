@@ -93,6 +93,8 @@ def main():
     ap.add_argument("--mode", default="both", choices=["test", "model", "both"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--no-int8-pipeline", action="store_true",
+                    help="ReconModel: keep the reference's fp32 NCHW module boundaries only")
     args = ap.parse_args()
     real_stdout, sys.stdout = sys.stdout, sys.stderr
     import tools
@@ -126,32 +128,49 @@ def main():
         if mode == "test":   # the caller fake-quantises the image itself (resnet_reconstruction.py:135)
             from common.quantity import QuanDequan
             x = QuanDequan(8, info["image"]["output_bit"])(x)
-        ms, stats, launches, y = timed_forward(model, x, args.iters)
-        line = {"metric": "ReconTest images/sec" if mode == "test" else "ReconModel images/sec",
-                "value": round(batch / (ms * 1e-3), 1), "unit": "images/s", "ms_per_forward": round(ms, 3),
-                "config": {"workload": "%s 224x224 %s, batch %d" % (model_name, "ReconTest" if mode == "test" else "ReconModel", batch)},
-                "gpu_launches_per_forward": launches, "kernels": {}}
-        for name, st in stats.items():
-            k = dict(st)
-            k["ms_per_fwd"] = round(k["ms_per_fwd"], 4)
-            if name == "fakequant":
-                k["GBps"] = round(st["alg_bytes_per_fwd"] / (st["ms_per_fwd"] * 1e-3) / 1e9, 1)
-                k["frac_of_hbm_peak"] = round(k["GBps"] / peak_hbm, 4)
-            line["kernels"][name] = k
-        if mode == "model":
-            peak = int8_peak_tops()
-            ops = sum(st.get("alg_ops_per_fwd", 0) for st in stats.values())
-            line["int8_peak_TOPS_measured"] = round(peak, 1)
-            for name in ("conv_s8", "gemm_s8"):
-                if name in stats and stats[name]["ms_per_fwd"] > 0:
-                    tops = stats[name]["alg_bytes_per_fwd"] / (stats[name]["ms_per_fwd"] * 1e-3) / 1e12
-                    line["kernels"][name]["TOPS"] = round(tops, 1)
-                    line["kernels"][name]["frac_of_int8_peak"] = round(tops / peak, 4)
-        assert torch.isfinite(y).all()
-        lines.append(line)
+        variants = [("fp32 module boundaries (reference semantics)", False)]
+        if mode == "model" and not args.no_int8_pipeline:
+            variants.append(("int8 inter-layer pipeline (bit-identical output)", True))
+        y_ref = None
+        for label, pipe in variants:
+            if mode == "model":
+                from common.quantity import enable_int8_pipeline
+                enable_int8_pipeline(model, pipe)
+            ms, stats, launches, y = timed_forward(model, x, args.iters)
+            if y_ref is None:
+                y_ref = y
+            assert torch.equal(y, y_ref), "pipeline output differs"
+            line = emit_line(mode, model_name, batch, label, ms, stats, launches, peak_hbm)
+            assert torch.isfinite(y).all()
+            lines.append(line)
     sys.stdout = real_stdout
     for line in lines:
         print(json.dumps(line), flush=True)
+
+
+def emit_line(mode, model_name, batch, label, ms, stats, launches, peak_hbm):
+    line = {"metric": "ReconTest images/sec" if mode == "test" else "ReconModel images/sec",
+            "value": round(batch / (ms * 1e-3), 1), "unit": "images/s", "ms_per_forward": round(ms, 3),
+            "config": {"workload": "%s 224x224 %s, batch %d" % (model_name, "ReconTest" if mode == "test" else "ReconModel", batch),
+                       "variant": label},
+            "gpu_launches_per_forward": launches, "kernels": {}}
+    for name, st in stats.items():
+        k = dict(st)
+        k["ms_per_fwd"] = round(k["ms_per_fwd"], 4)
+        if name in ("fakequant", "add_clamp", "quantize_s8", "relu_s8", "maxpool_s8", "add_requant"):
+            k["GBps"] = round(st["alg_bytes_per_fwd"] / (st["ms_per_fwd"] * 1e-3) / 1e9, 1)
+            k["frac_of_hbm_peak"] = round(k["GBps"] / peak_hbm, 4)
+        line["kernels"][name] = k
+    if mode == "model":
+        peak = int8_peak_tops()
+        line["int8_peak_TOPS_measured"] = round(peak, 1)
+        for name in ("conv_s8", "gemm_s8"):
+            if name in stats and stats[name]["ms_per_fwd"] > 0:
+                tops = stats[name]["alg_bytes_per_fwd"] / (stats[name]["ms_per_fwd"] * 1e-3) / 1e12
+                line["kernels"][name]["int8_ops_per_fwd"] = line["kernels"][name].pop("alg_bytes_per_fwd")
+                line["kernels"][name]["TOPS"] = round(tops, 1)
+                line["kernels"][name]["frac_of_int8_peak"] = round(tops / peak, 4)
+    return line
 
 
 if __name__ == "__main__":

@@ -137,6 +137,34 @@ int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias
                  const pq_conv_desc *desc_host, float *out_f32_nchw, int8_t *out_s8_nhwc,
                  pq_stream_t stream);
 
+/* ---- SURVEY 8(f) n1, the int8 inter-layer pipeline (no reference counterpart as separate ops; the
+ * composition is bit-identical to the reference's fp32-boundary chain because a layer's input_bit is
+ * its producer's output_bit in feat.table, tools/pytorch_quantizer.py:468-485).
+ * PQ_FLAG_RELU fuses a following nn.ReLU into the GEMM / conv epilogue: y = max(y, 0). */
+#define PQ_FLAG_RELU 1
+int pq_gemm_s8_ex(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs,
+                  int ob, int hw, int flags, float *out_f32, int8_t *out_s8, pq_stream_t stream);
+int pq_conv2d_s8_ex(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
+                    const pq_conv_desc *desc_host, int flags, float *out_f32_nchw, int8_t *out_s8_nhwc,
+                    pq_stream_t stream);
+
+/* y = max(x, 0) on int8 (nn.ReLU on a quantised tensor: relu commutes with the input quantiser). */
+int pq_relu_s8(const int8_t *x, int8_t *y, size_t n, pq_stream_t stream);
+
+/* nn.MaxPool2d on int8 NHWC (max commutes with the monotone quantiser); relu != 0 also applies max(.,0).
+ * Padding behaves like -inf, as in torch. */
+int pq_maxpool_nhwc_s8(const int8_t *x, int8_t *y, int N, int H, int W, int C, int k, int stride, int pad,
+                       int relu, pq_stream_t stream);
+
+/* NewAdd.forward (new_quantity_op.py:166-174) on quantised operands, exactly:
+ *   s = clamp(a / 2^a_bit + b / 2^b_bit, -128, 127)       a, b: int8 or int16 (a_is16 / b_is16),
+ *                                                           a_relu / b_relu apply max(.,0) on load
+ *   out16 = s * 2^o_bit (int16, o_bit = max(a_bit, b_bit), exact)      -> the identity shortcut of the next add
+ *   out8  = clamp(round_half_even(s * 2^q_bit), -128, 127) (int8)      -> Quantity(q_bit) of the consuming convs
+ * Either output may be NULL.  Requires 0 <= o_bit - min(a_bit, b_bit) <= 7 and |q_bit - o_bit| <= 15. */
+int pq_add_requant(const void *a, int a_is16, int a_bit, int a_relu, const void *b, int b_is16, int b_bit,
+                   int b_relu, size_t n, int16_t *out16, int8_t *out8, int q_bit, pq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,7 +36,13 @@ SYMBOLS = {
     "pq_quantize_im2col_s8": (_i, [_vp, _vp] + [_i] * 12 + [_vp]),
     "pq_gemm_s8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pq_conv2d_s8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pq_gemm_s8_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "pq_conv2d_s8_ex": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "pq_relu_s8": (_i, [_vp, _vp, _sz, _vp]),
+    "pq_maxpool_nhwc_s8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "pq_add_requant": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _sz, _vp, _vp, _i, _vp]),
 }
+FLAG_RELU = 1
 
 
 class ConvDesc(ctypes.Structure):
@@ -245,7 +251,7 @@ def quantize_im2col_s8(x, ib, kernel, stride, padding, kp):
     return a, (N, P, Q)
 
 
-def gemm_s8(a, w, bias_q, rs, ob, hw=1, want_f32=True, want_s8=False, k_real=None):
+def gemm_s8(a, w, bias_q, rs, ob, hw=1, want_f32=True, want_s8=False, k_real=None, relu=False):
     """a int8 [M][K], w int8 [N][K], bias_q int32 [N] -> fp32 (NCHW with hw pixels per image,
     or [M][N] when hw == 1) and / or int8 [M][N]."""
     require_cuda(a, "gemm_s8")
@@ -257,13 +263,14 @@ def gemm_s8(a, w, bias_q, rs, ob, hw=1, want_f32=True, want_s8=False, k_real=Non
     if want_s8:
         out_s8 = torch.empty((M, N), dtype=torch.int8, device=a.device)
     with _Timed("gemm_s8", 1, 2 * M * N * (k_real or K), a.device):      # "bytes" field carries int8 ops here
-        check(lib().pq_gemm_s8(a.data_ptr(), w.data_ptr(), bias_q.data_ptr(), M, N, K, int(rs), int(ob), hw,
-                               out_f32.data_ptr() if want_f32 else None,
-                               out_s8.data_ptr() if want_s8 else None, _stream(a)), "pq_gemm_s8")
+        check(lib().pq_gemm_s8_ex(a.data_ptr(), w.data_ptr(), bias_q.data_ptr(), M, N, K, int(rs), int(ob), hw,
+                                  FLAG_RELU if relu else 0, out_f32.data_ptr() if want_f32 else None,
+                                  out_s8.data_ptr() if want_s8 else None, _stream(a)), "pq_gemm_s8")
     return out_f32, out_s8
 
 
-def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, want_s8=False, c_real=None):
+def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, want_s8=False, c_real=None,
+              relu=False):
     require_cuda(x_nhwc, "conv2d_s8")
     N, H, W, C = x_nhwc.shape
     K, R, S, C2 = w_krsc.shape
@@ -274,7 +281,43 @@ def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, wa
     out_f32 = torch.empty((N, K, P, Q), dtype=torch.float32, device=x_nhwc.device) if want_f32 else None
     out_s8 = torch.empty((N, P, Q, K), dtype=torch.int8, device=x_nhwc.device) if want_s8 else None
     with _Timed("conv_s8", 1, 2 * N * P * Q * K * R * S * (c_real or C), x_nhwc.device):   # int8 ops
-        check(lib().pq_conv2d_s8(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
-                                 out_f32.data_ptr() if want_f32 else None,
-                                 out_s8.data_ptr() if want_s8 else None, _stream(x_nhwc)), "pq_conv2d_s8")
+        check(lib().pq_conv2d_s8_ex(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
+                                    FLAG_RELU if relu else 0, out_f32.data_ptr() if want_f32 else None,
+                                    out_s8.data_ptr() if want_s8 else None, _stream(x_nhwc)), "pq_conv2d_s8")
     return out_f32, out_s8
+
+
+def relu_s8(x):
+    require_cuda(x, "relu_s8")
+    xc = x.contiguous()
+    y = torch.empty_like(xc)
+    with _Timed("relu_s8", 1, 2 * xc.numel(), xc.device):
+        check(lib().pq_relu_s8(xc.data_ptr(), y.data_ptr(), xc.numel(), _stream(xc)), "pq_relu_s8")
+    return y
+
+
+def maxpool_nhwc_s8(x, k, stride, pad, relu=False):
+    require_cuda(x, "maxpool_nhwc_s8")
+    N, H, W, C = x.shape
+    P = (H + 2 * pad - k) // stride + 1
+    Q = (W + 2 * pad - k) // stride + 1
+    y = torch.empty((N, P, Q, C), dtype=torch.int8, device=x.device)
+    with _Timed("maxpool_s8", 1, x.numel() + y.numel(), x.device):
+        check(lib().pq_maxpool_nhwc_s8(x.data_ptr(), y.data_ptr(), N, H, W, C, k, stride, pad, 1 if relu else 0,
+                                       _stream(x)), "pq_maxpool_nhwc_s8")
+    return y
+
+
+def add_requant(a, a_bit, a_relu, b, b_bit, b_relu, q_bit, want16=True, want8=True):
+    """Exact NewAdd on quantised operands (int8 or int16 tensors of identical shape)."""
+    require_cuda(a, "add_requant")
+    assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    out16 = torch.empty(a.shape, dtype=torch.int16, device=a.device) if want16 else None
+    out8 = torch.empty(a.shape, dtype=torch.int8, device=a.device) if want8 else None
+    nbytes = a.numel() * (a.element_size() + b.element_size() + (2 if want16 else 0) + (1 if want8 else 0))
+    with _Timed("add_requant", 1, nbytes, a.device):
+        check(lib().pq_add_requant(a.data_ptr(), 1 if a.dtype == torch.int16 else 0, int(a_bit), 1 if a_relu else 0,
+                                   b.data_ptr(), 1 if b.dtype == torch.int16 else 0, int(b_bit), 1 if b_relu else 0,
+                                   a.numel(), out16.data_ptr() if want16 else None,
+                                   out8.data_ptr() if want8 else None, int(q_bit), _stream(a)), "pq_add_requant")
+    return out16, out8

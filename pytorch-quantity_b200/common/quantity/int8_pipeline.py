@@ -1,0 +1,199 @@
+"""Int8 inter-layer pipeline for the integer simulation (opt-in).
+
+The reference's ``NewConv2d`` de-quantises its result to fp32 NCHW and the next ``NewConv2d``
+quantises it again (new_quantity_op.py:124-133).  In feat.table a layer's input bit IS its producer's
+output bit (tools/pytorch_quantizer.py:468-485), so that round trip is the identity on the int8
+values: ``Quantity(ib)(y / 2^ob) == y`` when ``ib == ob``.  With the pipeline enabled the tensor-core
+layers hand each other int8 NHWC payloads wrapped in a lazy ``QTensor``:
+
+    NewConv2d -> QTensor(int8 NHWC, bit)            epilogue stores int8 (ReLU fused when it follows)
+    nn.ReLU / nn.MaxPool2d on a QTensor             stay int8 (both commute with the monotone quantiser)
+    NewAdd(QTensor, QTensor)                        exact integer sum: int16 (for the next identity
+                                                    shortcut) + int8 at the Eltwise's feat bit (for convs)
+    anything else (AvgPool2d, Concat, user code)    the QTensor de-quantises itself to fp32 NCHW first
+
+so the final output is bit-identical to the fp32-boundary model while HBM traffic drops ~4x.
+``enable_int8_pipeline(model)`` turns it on for a model built by ``Reconstruction.ReconModel``.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native
+
+
+_METADATA = {"__get__", "size", "dim", "numel", "element_size", "ndimension", "is_floating_point", "__len__",
+             "get_device", "is_complex", "nelement"}
+
+
+class QTensor(torch.Tensor):
+    """A float32 NCHW tensor that exists only as quantised payloads until somebody needs the floats."""
+
+    @staticmethod
+    def __new__(cls, shape, device, **kw):
+        return torch.Tensor._make_wrapper_subclass(cls, shape, dtype=torch.float32, device=device,
+                                                   requires_grad=False)
+
+    def __init__(self, shape, device, q8=None, q8_bit=None, s16=None, s16_bit=None, relu_pending=False,
+                 nonneg=False):
+        self.q8, self.q8_bit = q8, q8_bit              # int8 NHWC, value = q8 / 2^q8_bit (after pending relu)
+        self.s16, self.s16_bit = s16, s16_bit          # int16 NHWC exact value (outputs of NewAdd)
+        self.relu_pending = relu_pending               # a ReLU was applied logically but not to the payloads
+        self.nonneg = nonneg                           # payloads are already >= 0
+        self._q8_relu = None
+
+    def __repr__(self):
+        return "QTensor(shape=%s, q8_bit=%s, s16_bit=%s, relu_pending=%s)" % (
+            tuple(self.shape), self.q8_bit, self.s16_bit, self.relu_pending)
+
+    # ---- payload access -------------------------------------------------------------------
+    def int8_payload(self):
+        """int8 NHWC with any pending ReLU applied (materialised once)."""
+        if not self.relu_pending or self.nonneg:
+            return self.q8
+        if self._q8_relu is None:
+            self._q8_relu = _native.relu_s8(self.q8)
+        return self._q8_relu
+
+    def dequantize(self):
+        """fp32 NCHW, exactly what the fp32-boundary model would hold here (cold path: plain torch ops)."""
+        if self.s16 is not None:
+            v = self.s16.to(torch.float32) * (2.0 ** -self.s16_bit)
+        else:
+            v = self.q8.to(torch.float32) * (2.0 ** -self.q8_bit)
+        if self.relu_pending and not self.nonneg:
+            v = torch.relu(v)
+        return v.permute(0, 3, 1, 2).contiguous()
+
+    def with_relu(self):
+        if self.nonneg:
+            return self
+        return QTensor(self.shape, self.device, q8=self.q8, q8_bit=self.q8_bit, s16=self.s16,
+                       s16_bit=self.s16_bit, relu_pending=True)
+
+    # ---- dispatch -------------------------------------------------------------------------
+    @classmethod
+    def __torch_dispatch__(cls, func, types, args=(), kwargs=None):
+        # ATen-level calls that slipped past __torch_function__: compute on the de-quantised floats
+        return func(*_plain_tree(args), **_plain_tree(kwargs or {}))
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func in (F.relu, torch.relu, torch.Tensor.relu) and isinstance(args[0], QTensor) \
+                and not kwargs.get("inplace", False) and len(args) == 1:
+            return args[0].with_relu()
+        if func is F.max_pool2d and isinstance(args[0], QTensor):
+            out = _maxpool(args[0], *args[1:], **kwargs)
+            if out is not None:
+                return out
+        # metadata queries are answered by the wrapper itself (no payload is touched)
+        if getattr(func, "__name__", "") in _METADATA:
+            with torch._C.DisableTorchFunctionSubclass():
+                return func(*args, **kwargs)
+
+        def plain(a):
+            if isinstance(a, QTensor):
+                return a.dequantize()
+            if isinstance(a, (list, tuple)):
+                return type(a)(plain(v) for v in a)
+            return a
+
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*plain(args), **{k: plain(v) for k, v in kwargs.items()})
+
+
+def _plain_tree(obj):
+    from torch.utils._pytree import tree_map
+    return tree_map(lambda a: a.dequantize() if isinstance(a, QTensor) else a, obj)
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def _maxpool(x, kernel_size, stride=None, padding=0, dilation=1, ceil_mode=False, return_indices=False):
+    k, s, p = _pair(kernel_size), _pair(stride if stride is not None else kernel_size), _pair(padding)
+    if k[0] != k[1] or s[0] != s[1] or p[0] != p[1] or _pair(dilation) != (1, 1) or ceil_mode or return_indices:
+        return None
+    if x.q8 is None or x.q8.shape[-1] % 16:
+        return None
+    relu = x.relu_pending and not x.nonneg
+    y = _native.maxpool_nhwc_s8(x.q8, k[0], s[0], p[0], relu=relu)
+    N, P, Q, C = y.shape
+    return QTensor((N, x.shape[1], P, Q), x.device, q8=y, q8_bit=x.q8_bit, nonneg=x.nonneg or relu)
+
+
+def conv_forward(mod, x):
+    """NewConv2d.forward in pipeline mode."""
+    conv = mod.Conv
+    if isinstance(x, QTensor):
+        usable = (x.q8 is not None and x.q8_bit == mod.input_bit and not mod._explicit_im2col
+                  and x.q8.shape[-1] == mod._c_pad)
+        if not usable:
+            x = x.dequantize()
+    if isinstance(x, QTensor):
+        q = x.int8_payload()                                     # Quantity(ib) is the identity here
+    elif mod._explicit_im2col:
+        a, (N, P, Q) = _native.quantize_im2col_s8(x, mod.input_bit, conv.kernel_size, conv.stride,
+                                                  conv.padding, mod._k_pad)
+        _, out8 = _native.gemm_s8(a, mod._w_nk, mod._bias_i32, mod.rs_bit, mod.output_bit, hw=1,
+                                  want_f32=False, want_s8=True, relu=mod._fuse_relu,
+                                  k_real=conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1])
+        return QTensor((N, conv.out_channels, P, Q), out8.device, q8=out8.view(N, P, Q, conv.out_channels),
+                       q8_bit=mod.output_bit, nonneg=mod._fuse_relu)
+    else:
+        q = _native.quantize_nchw_to_nhwc_s8(x, mod.input_bit, mod._c_pad)
+    _, out8 = _native.conv2d_s8(q, mod._w_krsc, mod._bias_i32, conv.stride, conv.padding, mod.rs_bit,
+                                mod.output_bit, want_f32=False, want_s8=True, c_real=conv.in_channels,
+                                relu=mod._fuse_relu)
+    N, P, Q, K = out8.shape
+    return QTensor((N, K, P, Q), out8.device, q8=out8, q8_bit=mod.output_bit, nonneg=mod._fuse_relu)
+
+
+def _operand(t):
+    """(payload, bit, relu) of the most exact representation of a QTensor."""
+    relu = t.relu_pending and not t.nonneg
+    if t.s16 is not None:
+        return t.s16, t.s16_bit, relu
+    return t.q8, t.q8_bit, relu
+
+
+def add_forward(mod, x, y):
+    """NewAdd.forward in pipeline mode; returns None when the operands are not both quantised."""
+    if not (isinstance(x, QTensor) and isinstance(y, QTensor)) or x.shape != y.shape:
+        return None
+    q_bit = getattr(mod, "output_bit", None)
+    (a, abit, arelu), (b, bbit, brelu) = _operand(x), _operand(y)
+    o_bit = max(abit, bbit)
+    if q_bit is None or a.shape != b.shape or not (0 <= o_bit <= 7) or o_bit - min(abit, bbit) > 7 \
+            or abs(q_bit - o_bit) > 15:
+        return None
+    s16, q8 = _native.add_requant(a, abit, arelu, b, bbit, brelu, q_bit)
+    return QTensor(x.shape, x.device, q8=q8, q8_bit=q_bit, s16=s16, s16_bit=o_bit)
+
+
+def enable_int8_pipeline(model, enabled=True):
+    """Switch a ReconModel to the int8 inter-layer pipeline (or back).  Also marks every NewConv2d that
+    is directly followed by an nn.ReLU inside an nn.Sequential (Identity modules in between are
+    skipped) so that its epilogue applies the ReLU."""
+    from .fabu_layer import Identity
+    from .new_quantity_op import NewAdd, NewConv2d
+    for m in model.modules():
+        if isinstance(m, (NewConv2d, NewAdd)):
+            m.int8_pipeline = enabled
+        if isinstance(m, NewConv2d):
+            m._fuse_relu = False
+    if enabled:
+        for seq in model.modules():
+            if not isinstance(seq, nn.Sequential):
+                continue
+            kids = list(seq.children())
+            for i, k in enumerate(kids):
+                if isinstance(k, NewConv2d):
+                    j = i + 1
+                    while j < len(kids) and isinstance(kids[j], Identity):
+                        j += 1
+                    if j < len(kids) and isinstance(kids[j], nn.ReLU):
+                        k._fuse_relu = True
+    return model

@@ -149,6 +149,8 @@ class NewConv2d(_IntSimBase):
         super().__init__()
         self._read_info(quantize_infor)
         self.Conv = conv_module
+        self.int8_pipeline = False      # see int8_pipeline.enable_int8_pipeline
+        self._fuse_relu = False
         self.quantity()
 
     def quantity(self):
@@ -173,6 +175,9 @@ class NewConv2d(_IntSimBase):
         self.register_buffer("_w_krsc", w_krsc.contiguous())
 
     def forward(self, input):
+        if getattr(self, "int8_pipeline", False):
+            from .int8_pipeline import conv_forward
+            return conv_forward(self, input)
         conv = self.Conv
         if self._explicit_im2col:
             a, (N, P, Q) = _native.quantize_im2col_s8(input, self.input_bit, conv.kernel_size, conv.stride,
@@ -223,6 +228,11 @@ class NewAdd(nn.Module):
         self.Sp = Sp(QUANTIZE_BIT)
 
     def forward(self, x, y):
+        if getattr(self, "int8_pipeline", False):
+            from .int8_pipeline import add_forward
+            out = add_forward(self, x, y)
+            if out is not None:
+                return out
         lo, hi = _range(QUANTIZE_BIT)
         return _native.add_clamp(x, y, lo, hi).view(torch.broadcast_shapes(x.shape, y.shape))
 

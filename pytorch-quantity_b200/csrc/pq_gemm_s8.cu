@@ -161,6 +161,7 @@ struct GemmParams {
     int stride_h, stride_w, pad_h, pad_w;
     int rs, ob;                // RightShift amount, output fractional bit
     int hw;                    // pixels per image for the fp32 NCHW store (1: plain [M][N])
+    int relu;                  // int8 pipeline: apply max(y, 0) in the epilogue (a following nn.ReLU)
     const int32_t *bias;       // [N] quantised bias (already saturated to int8 range)
     float *out_f32;            // optional
     int8_t *out_s8;            // optional, [M][N]
@@ -170,12 +171,13 @@ struct GemmParams {
 //   rs >= 1:  round_half_away(acc / 2^rs) = (acc + 2^(rs-1) - (acc < 0)) >> rs   (arithmetic shift)
 //   rs <= 0:  acc * 2^-rs, saturated first (the shift is monotone)
 struct Requant {
-    int half, sh, mul;         // rs >= 1: half = 2^(rs-1), sh = rs, mul unused; rs <= 0: mul = 2^-rs
+    int half, sh, mul, lo;     // rs >= 1: half = 2^(rs-1), sh = rs, mul unused; rs <= 0: mul = 2^-rs
     bool pos;
 };
-__device__ __forceinline__ Requant make_requant(int rs)
+__device__ __forceinline__ Requant make_requant(int rs, int relu)
 {
     Requant q;
+    q.lo = relu ? 0 : -128;
     q.pos = rs >= 1;
     q.half = rs >= 1 ? (1 << (rs - 1)) : 0;
     q.sh = rs >= 1 ? rs : 0;
@@ -188,7 +190,7 @@ __device__ __forceinline__ int requant(int acc, const Requant &q, int bias)
     if (q.pos) r = (acc + q.half + (acc >> 31)) >> q.sh;
     else r = max(-128, min(127, acc)) * q.mul;
     r = max(-128, min(127, r));
-    return max(-128, min(127, r + bias));
+    return max(q.lo, min(127, r + bias));          // q.lo = -128, or 0 when a ReLU is fused
 }
 
 template <int BN, int BK, int STAGES>
@@ -299,7 +301,7 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         constexpr int kChunk = kCols < 16 ? kCols : 16;
         constexpr int kChunks = kCols / kChunk;
         const int row = quad * 32 + lane;
-        const Requant rq = make_requant(p.rs);
+        const Requant rq = make_requant(p.rs, p.relu);
         const float dq = __int_as_float((127 - p.ob) << 23);        // 2^-ob, exact
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -533,8 +535,17 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const pq::GemmParams &p
 
 }  // namespace
 
+extern "C" int pq_gemm_s8_ex(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs,
+                             int ob, int hw, int flags, float *out_f32, int8_t *out_s8, pq_stream_t stream);
+
 extern "C" int pq_gemm_s8(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs,
                           int ob, int hw, float *out_f32, int8_t *out_s8, pq_stream_t stream)
+{
+    return pq_gemm_s8_ex(a, w, bias_q, M, N, K, rs, ob, hw, 0, out_f32, out_s8, stream);
+}
+
+extern "C" int pq_gemm_s8_ex(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs,
+                             int ob, int hw, int flags, float *out_f32, int8_t *out_s8, pq_stream_t stream)
 {
     if (M <= 0 || N <= 0 || K <= 0 || hw <= 0) return PQ_EINVAL;
     if (!a || !w || !bias_q || (!out_f32 && !out_s8)) return PQ_EINVAL;
@@ -551,12 +562,20 @@ extern "C" int pq_gemm_s8(const int8_t *a, const int8_t *w, const int32_t *bias_
     pq::GemmParams p = {};
     p.M = M; p.N = N; p.num_kb = (K + bk - 1) / bk; p.a_im2col = 0;
     p.rs = rs; p.ob = ob; p.hw = hw; p.bias = bias_q; p.out_f32 = out_f32; p.out_s8 = out_s8;
+    p.relu = flags & PQ_FLAG_RELU;
     return launch(ta, tb, p, bk, bn, (cudaStream_t)stream);
 }
 
 extern "C" int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
                             const pq_conv_desc *desc_host, float *out_f32_nchw, int8_t *out_s8_nhwc,
                             pq_stream_t stream)
+{
+    return pq_conv2d_s8_ex(x_nhwc, w_krsc, bias_q, desc_host, 0, out_f32_nchw, out_s8_nhwc, stream);
+}
+
+extern "C" int pq_conv2d_s8_ex(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
+                               const pq_conv_desc *desc_host, int flags, float *out_f32_nchw,
+                               int8_t *out_s8_nhwc, pq_stream_t stream)
 {
     if (!x_nhwc || !w_krsc || !bias_q || !desc_host || (!out_f32_nchw && !out_s8_nhwc)) return PQ_EINVAL;
     const pq_conv_desc &d = *desc_host;
@@ -570,8 +589,8 @@ extern "C" int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const in
     const long long M = (long long)d.N * d.P * d.Q;
     if (M > 0x7fffffffLL) return PQ_EUNSUPPORTED;
     if (d.R == 1 && d.S == 1 && d.stride_h == 1 && d.stride_w == 1 && d.pad_h == 0 && d.pad_w == 0)
-        return pq_gemm_s8(x_nhwc, w_krsc, bias_q, (int)M, d.K, d.C, d.rs, d.ob, d.P * d.Q, out_f32_nchw,
-                          out_s8_nhwc, stream);                      // 1x1 stride-1: a plain GEMM over NHWC
+        return pq_gemm_s8_ex(x_nhwc, w_krsc, bias_q, (int)M, d.K, d.C, d.rs, d.ob, d.P * d.Q, flags, out_f32_nchw,
+                             out_s8_nhwc, stream);                   // 1x1 stride-1: a plain GEMM over NHWC
     if (d.C & 31) return PQ_EUNSUPPORTED;                            // im2col path: channel blocks of >= 32
     int rc = load_driver_entry_points();
     if (rc != PQ_OK) return rc;
@@ -586,5 +605,6 @@ extern "C" int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const in
     p.R = d.R; p.S = d.S; p.C = d.C; p.cblocks = d.C / bk; p.num_kb = d.R * d.S * p.cblocks;
     p.P = d.P; p.Q = d.Q; p.stride_h = d.stride_h; p.stride_w = d.stride_w; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
     p.rs = d.rs; p.ob = d.ob; p.hw = d.P * d.Q; p.bias = bias_q; p.out_f32 = out_f32_nchw; p.out_s8 = out_s8_nhwc;
+    p.relu = flags & PQ_FLAG_RELU;
     return launch(ta, tb, p, bk, bn, (cudaStream_t)stream);
 }

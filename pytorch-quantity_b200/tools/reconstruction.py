@@ -75,6 +75,7 @@ class Reconstruction(object):
                 new = make_linear(name, module, all_quantize_infor[name])
             else:
                 new = NewAdd()
+                new.output_bit = all_quantize_infor[name]["output_bit"]   # feat bit of the Eltwise (int8 pipeline)
             _swap(self.model, name, new)
             print("The layer change: {} ==>{} ".format(name, type(new).__name__))
         print("Model reconstruction successfully !")

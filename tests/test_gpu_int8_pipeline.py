@@ -1,0 +1,130 @@
+"""The int8 inter-layer pipeline must be bit-identical to the fp32-boundary ReconModel,
+which in turn is pinned to the reference (tests/test_gpu_intsim.py).  Also unit-tests its kernels
+against exact integer / torch restatements."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden_json, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_relu_and_maxpool_s8():
+    from common.quantity import _native
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randint(-128, 128, (3, 17, 19, 32), dtype=torch.int8, device="cuda", generator=g)
+    assert torch.equal(_native.relu_s8(x), torch.clamp(x, min=0))
+    flat = torch.randint(-128, 128, (1000003,), dtype=torch.int8, device="cuda", generator=g)[3:]   # odd size
+    assert torch.equal(_native.relu_s8(flat.clone()), torch.clamp(flat, min=0))
+    for (k, s, p) in [(3, 2, 1), (2, 2, 0), (3, 1, 1)]:
+        for relu in (False, True):
+            y = _native.maxpool_nhwc_s8(x, k, s, p, relu=relu)
+            ref = F.max_pool2d(x.permute(0, 3, 1, 2).float(), k, s, p)
+            if relu:
+                ref = torch.relu(ref)
+            assert torch.equal(y.permute(0, 3, 1, 2).float(), ref), (k, s, p, relu)
+
+
+@pytest.mark.parametrize("abit,bbit,qbit,a16,b16", [(4, 4, 4, False, False), (5, 3, 4, False, False), (3, 6, 7, False, True),
+                                                    (6, 6, 2, True, True), (2, 7, 0, True, False), (0, 0, 5, False, False)])
+def test_add_requant_exact(abit, bbit, qbit, a16, b16):
+    from common.quantity import _native
+    rng = np.random.default_rng(abit * 100 + bbit * 10 + qbit)
+    n = 100003 + 5
+    def operand(is16, bit):
+        lim = 127 * 2 ** bit if is16 else 127
+        lo = -128 * 2 ** bit if is16 else -128
+        return rng.integers(lo, lim + 1, size=n).astype(np.int16 if is16 else np.int8)
+    a, b = operand(a16, abit), operand(b16, bbit)
+    for arelu, brelu in ((False, False), (True, False), (True, True)):
+        av = np.maximum(a, 0) if arelu else a
+        bv = np.maximum(b, 0) if brelu else b
+        # the reference's arithmetic: fp32 sum of the real values, clamp, then the consumer's Quantity(q_bit)
+        s = np.clip(av.astype(np.float32) / np.float32(2 ** abit) + bv.astype(np.float32) / np.float32(2 ** bbit),
+                    np.float32(-128), np.float32(127))
+        o = max(abit, bbit)
+        ref16 = (s * np.float32(2 ** o)).astype(np.int64)
+        assert np.array_equal(ref16, s.astype(np.float64) * 2 ** o)          # exact
+        ref8 = np.clip(np.rint(s * np.float32(2.0 ** qbit)), -128, 127).astype(np.int64)
+        ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        o16, o8 = _native.add_requant(ta, abit, arelu, tb, bbit, brelu, qbit)
+        assert np.array_equal(o16.cpu().numpy().astype(np.int64), ref16)
+        assert np.array_equal(o8.cpu().numpy().astype(np.int64), ref8)
+
+
+def _build_recon(model_name, tmp_path, batch_shape):
+    import tools
+    from common.quantity import merge_bn
+    from bench_sim import build, configs
+    cfg, user = configs(str(tmp_path / "wd"), 2)
+    with torch.no_grad():
+        q = tools.Quantity(merge_bn(build(model_name), "cpu"), config=cfg, user_config=user, verbose=False)
+        cal = [(torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(1 + i)), None) for i in range(2)]
+        q.activation_quantize(cal)
+        q.weight_quantize()
+        r = tools.Reconstruction(build(model_name), config=cfg)
+        r.merge_bn()
+        return r.ReconModel(r.get_quantity_information(), None).cuda().eval()
+
+
+@pytest.mark.parametrize("model_name,batch", [("r18", 3), ("r50", 2)])
+def test_pipeline_equals_fp32_boundary_model(tmp_path, model_name, batch):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from common.quantity import QTensor, enable_int8_pipeline, NewConv2d
+    model = _build_recon(model_name, tmp_path, batch)
+    x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(42)).cuda()
+    with torch.no_grad():
+        ref = model(x)
+        ref_layers = {}
+        hooks = [m.register_forward_hook(lambda m, i, o, n=n: ref_layers.__setitem__(n, o))
+                 for n, m in model.named_modules() if type(m).__name__ in ("NewConv2d", "NewAdd")]
+        model(x)
+        for h in hooks:
+            h.remove()
+        enable_int8_pipeline(model)
+        assert any(m._fuse_relu for m in model.modules() if isinstance(m, NewConv2d))
+        seen = {}
+        hooks = [m.register_forward_hook(lambda m, i, o, n=n: seen.__setitem__(n, o))
+                 for n, m in model.named_modules() if type(m).__name__ in ("NewConv2d", "NewAdd")]
+        out = model(x)
+        for h in hooks:
+            h.remove()
+    assert not isinstance(out, QTensor)
+    assert torch.equal(out, ref)
+    n_q = 0
+    for name, o in seen.items():
+        if isinstance(o, QTensor):
+            n_q += 1
+            got = o.dequantize()
+            want = ref_layers[name]
+            if o.nonneg and type(dict(model.named_modules())[name]).__name__ == "NewConv2d":
+                want = torch.relu(want)          # the ReLU that follows was fused into this epilogue
+            assert torch.equal(got, want), name
+    assert n_q >= 15
+    enable_int8_pipeline(model, False)
+    with torch.no_grad():
+        assert torch.equal(model(x), ref)
+
+
+def test_pipeline_fallback_paths_tiny_net(tmp_path):
+    """8-channel layers, Concat and odd shapes force the de-quantise fallbacks; the result must not change."""
+    import tools
+    from common.quantity import enable_int8_pipeline
+    from test_gpu_e2e import _configs, _tiny_model
+    g = load_golden("tiny_e2e.npz")
+    j = golden_json(g)
+    cfg, user = _configs(tmp_path, (1, 3, 16, 16), 2)
+    os.makedirs(cfg["OUTPUT"]["WORK_DIR"], exist_ok=True)
+    open(cfg["OUTPUT"]["FEAT_BIT_TABLE"], "w").write(j["after_second_rewrite"]["feat.table"])
+    open(cfg["OUTPUT"]["WEIGHT_BIT_TABLE"], "w").write(j["after_second_rewrite"]["weight.table"])
+    with torch.no_grad():
+        r = tools.Reconstruction(_tiny_model(g), config=cfg)
+        r.merge_bn()
+        model = enable_int8_pipeline(r.ReconModel(r.get_quantity_information(), None).cuda())
+        y = model(torch.from_numpy(g["eval_batch"]).cuda())
+    assert np.array_equal(y.cpu().numpy(), g["ReconModel/y"])
