@@ -38,11 +38,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--s8-out", action="store_true", help="store int8 NHWC instead of fp32 NCHW")
+    ap.add_argument("--only", type=int, default=None, help="run only this row of the table (for ncu captures)")
     args = ap.parse_args()
     B = args.batch
     tot_conv = tot_q = tot_ops = 0.0
     print("%-28s %9s %8s %8s %8s %8s %8s" % ("layer (Cin,H,W,Cout,k,s)xN", "GOP", "conv_ms", "TOPS", "outGB/s", "quant_ms", "qGB/s"))
-    for (cin, h, w, cout, k, s, cnt) in R50:
+    for (cin, h, w, cout, k, s, cnt) in (R50 if args.only is None else [R50[args.only]]):
         pad = k // 2
         plain = k == 1 and s == 1
         cpad = (cin + 15) // 16 * 16 if plain else (cin + 31) // 32 * 32

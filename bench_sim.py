@@ -62,13 +62,13 @@ def int8_peak_tops():
 
 
 def timed_forward(model, x, iters):
+    """ms per forward (clean, CUDA events around `iters` forwards) + per-kernel statistics from a second,
+    instrumented set of forwards (an event pair around every C-ABI launch)."""
     from common.quantity import _native
     with torch.no_grad():
         for _ in range(3):
             model(x)
         torch.cuda.synchronize()
-        prof = {}
-        _native.set_profile(prof)
         l0 = _native.LAUNCHES["total"]
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
@@ -76,15 +76,37 @@ def timed_forward(model, x, iters):
             y = model(x)
         e.record()
         torch.cuda.synchronize()
+        launches = (_native.LAUNCHES["total"] - l0) // iters
+        ms = s.elapsed_time(e) / iters
+        prof = {}
+        _native.set_profile(prof)
+        for _ in range(iters):
+            model(x)
+        torch.cuda.synchronize()
         _native.set_profile(None)
-    ms = s.elapsed_time(e) / iters
     stats = {}
     for name, rows in prof.items():
         t = [a.elapsed_time(b) for a, b, _ in rows]
         nb = [c for _, _, c in rows]
         stats[name] = {"launches_per_fwd": len(rows) // iters, "ms_per_fwd": sum(t) / iters,
                        "alg_bytes_per_fwd": sum(nb) / iters}
-    return ms, stats, (_native.LAUNCHES["total"] - l0) // iters, y
+    return ms, stats, launches, y
+
+
+def timed_graph(model, x, iters):
+    """The same forward captured once and replayed as a CUDA graph."""
+    from common.quantity import GraphedForward
+    fwd = GraphedForward(model, x)
+    for _ in range(3):
+        fwd(x)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        y = fwd(x)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters, fwd.launches, y.clone()
 
 
 def main():
@@ -143,6 +165,11 @@ def main():
             line = emit_line(mode, model_name, batch, label, ms, stats, launches, peak_hbm)
             assert torch.isfinite(y).all()
             lines.append(line)
+            if pipe:
+                gms, glaunches, gy = timed_graph(model, x, args.iters)
+                assert torch.equal(gy, y_ref), "graph replay output differs"
+                lines.append(emit_line(mode, model_name, batch, label + ", one CUDA graph per forward", gms, {},
+                                       glaunches, peak_hbm))
     sys.stdout = real_stdout
     for line in lines:
         print(json.dumps(line), flush=True)

@@ -111,6 +111,18 @@ int pq_quantize_im2col_s8(const float *x, int8_t *a, int N, int C, int H, int W,
                           int stride_h, int stride_w, int pad_h, int pad_w, int kp, int ib,
                           pq_stream_t stream);
 
+/* ---- a12 + a13 for convolutions with <= 8 input channels, fast form (the ResNet stem): the input
+ * quantiser writes a zero-padded NHWC image with 8-byte pixels,
+ *   q[n][h + pad_h][w + pad_w][c] = (int8) clamp(rint(x[n][c][h][w] * 2^ib)),  0 elsewhere   ([N][Hp][Wp][8])
+ * so that the S taps of one filter row are 8*S contiguous bytes; pq_conv2d_smallc_s8 fetches them for a
+ * patch of output pixels with one overlapping-stride tiled TMA per filter row (no im2col matrix in HBM).
+ * desc.C must be 8; weights are [K][R][64] int8 = 8 tap slots x 8 channel slots per filter row, zero
+ * where s >= S or c >= C.  Requires S <= 8, even stride_w, Hp % stride_h == 0,
+ * Hp >= max((P-1)*stride_h + R, H + pad_h), Wp even, Wp >= max((Q-1)*stride_w + 8, W + pad_w).
+ * Epilogue and outputs as pq_conv2d_s8_ex. */
+int pq_quantize_nchw_to_padded_nhwc8_s8(const float *x, int8_t *q, int N, int C, int H, int W, int pad_h,
+                                        int pad_w, int Hp, int Wp, int ib, pq_stream_t stream);
+
 /* ---- a13 + a14: NewConv2d.forward / NewLinear.forward, new_quantity_op.py:104-133,177-205
  * (Conv -> RightShift -> BiasAdd -> Sp -> DeQuantity) on int8 operands:
  *   acc  = sum_k a[m][k] * w[n][k]                 int8 x int8 -> int32 (tcgen05 kind::i8)
@@ -148,6 +160,10 @@ int pq_conv2d_s8_ex(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *b
                     const pq_conv_desc *desc_host, int flags, float *out_f32_nchw, int8_t *out_s8_nhwc,
                     pq_stream_t stream);
 
+int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const int32_t *bias_q,
+                        const pq_conv_desc *desc_host, int Hp, int Wp, int flags, float *out_f32_nchw,
+                        int8_t *out_s8_nhwc, pq_stream_t stream);
+
 /* y = max(x, 0) on int8 (nn.ReLU on a quantised tensor: relu commutes with the input quantiser). */
 int pq_relu_s8(const int8_t *x, int8_t *y, size_t n, pq_stream_t stream);
 
@@ -164,6 +180,11 @@ int pq_maxpool_nhwc_s8(const int8_t *x, int8_t *y, int N, int H, int W, int C, i
  * Either output may be NULL.  Requires 0 <= o_bit - min(a_bit, b_bit) <= 7 and |q_bit - o_bit| <= 15. */
 int pq_add_requant(const void *a, int a_is16, int a_bit, int a_relu, const void *b, int b_is16, int b_bit,
                    int b_relu, size_t n, int16_t *out16, int8_t *out8, int q_bit, pq_stream_t stream);
+/* flags & PQ_FLAG_RELU: the nn.ReLU that follows the Eltwise is applied to s before both outputs
+ * (max(.,0) commutes with the monotone quantiser, so out8 equals Quantity(q_bit)(relu(s))). */
+int pq_add_requant_ex(const void *a, int a_is16, int a_bit, int a_relu, const void *b, int b_is16, int b_bit,
+                      int b_relu, size_t n, int flags, int16_t *out16, int8_t *out8, int q_bit,
+                      pq_stream_t stream);
 
 #ifdef __cplusplus
 }

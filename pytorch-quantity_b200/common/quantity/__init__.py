@@ -9,7 +9,7 @@ from .fabu_layer import Eltwise, Concat, Identity, View
 from .new_quantity_op import (RightShift, Sp, BiasAdd, NewConv2d, NewAdd, NewLinear, QuanDequan,
                               TestConv, TestLinear, Quantity, DeQuantity)
 
-from .int8_pipeline import enable_int8_pipeline, QTensor    # extension, not a reference name
+from .int8_pipeline import enable_int8_pipeline, QTensor, GraphedForward   # extensions, not reference names
 
 __all__ = ["DistributionCollector", "Quantizer", "BitReader", "merge_bn", "walk_dirs", "tid",
            "Eltwise", "Concat", "Identity", "View", "RightShift", "Sp", "BiasAdd", "NewConv2d",

@@ -34,6 +34,8 @@ SYMBOLS = {
     "pq_clamp_scale_f32": (_i, [_vp, _vp, _sz, _f, _f, _f, _vp]),
     "pq_quantize_nchw_to_nhwc_s8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pq_quantize_im2col_s8": (_i, [_vp, _vp] + [_i] * 12 + [_vp]),
+    "pq_quantize_nchw_to_padded_nhwc8_s8": (_i, [_vp, _vp] + [_i] * 9 + [_vp]),
+    "pq_conv2d_smallc_s8": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pq_gemm_s8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pq_conv2d_s8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pq_gemm_s8_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -41,6 +43,7 @@ SYMBOLS = {
     "pq_relu_s8": (_i, [_vp, _vp, _sz, _vp]),
     "pq_maxpool_nhwc_s8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pq_add_requant": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _sz, _vp, _vp, _i, _vp]),
+    "pq_add_requant_ex": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _sz, _i, _vp, _vp, _i, _vp]),
 }
 FLAG_RELU = 1
 
@@ -251,6 +254,40 @@ def quantize_im2col_s8(x, ib, kernel, stride, padding, kp):
     return a, (N, P, Q)
 
 
+def quantize_pad_nhwc8_s8(x, ib, padding, Hp, Wp):
+    """fp32 NCHW (C <= 8) -> zero-padded int8 [N][Hp][Wp][8] for conv2d_smallc_s8."""
+    require_cuda(x, "quantize_pad_nhwc8_s8")
+    assert x.dim() == 4 and x.dtype == torch.float32
+    xc = x.contiguous()
+    N, C, H, W = xc.shape
+    q = torch.empty((N, Hp, Wp, 8), dtype=torch.int8, device=x.device)
+    with _Timed("quantize_s8", 1, xc.numel() * 4 + q.numel(), xc.device):
+        check(lib().pq_quantize_nchw_to_padded_nhwc8_s8(xc.data_ptr(), q.data_ptr(), N, C, H, W, padding[0],
+                                                        padding[1], Hp, Wp, int(ib), _stream(xc)),
+              "pq_quantize_nchw_to_padded_nhwc8_s8")
+    return q
+
+
+def conv2d_smallc_s8(xp, w_krs8, bias_q, in_hw, kernel, stride, padding, rs, ob, want_f32=True, want_s8=False,
+                     c_real=None, relu=False):
+    """xp int8 [N][Hp][Wp][8] (padded), w_krs8 int8 [K][R][64] -> fp32 NCHW and / or int8 NHWC."""
+    require_cuda(xp, "conv2d_smallc_s8")
+    N, Hp, Wp, _ = xp.shape
+    K = w_krs8.shape[0]
+    H, W = in_hw
+    R, S = kernel
+    P = (H + 2 * padding[0] - R) // stride[0] + 1
+    Q = (W + 2 * padding[1] - S) // stride[1] + 1
+    d = ConvDesc(N, H, W, 8, K, R, S, stride[0], stride[1], padding[0], padding[1], P, Q, int(rs), int(ob))
+    out_f32 = torch.empty((N, K, P, Q), dtype=torch.float32, device=xp.device) if want_f32 else None
+    out_s8 = torch.empty((N, P, Q, K), dtype=torch.int8, device=xp.device) if want_s8 else None
+    with _Timed("conv_s8", 1, 2 * N * P * Q * K * R * S * (c_real or 8), xp.device):        # int8 ops
+        check(lib().pq_conv2d_smallc_s8(xp.data_ptr(), w_krs8.data_ptr(), bias_q.data_ptr(), ctypes.byref(d), Hp, Wp,
+                                        FLAG_RELU if relu else 0, out_f32.data_ptr() if want_f32 else None,
+                                        out_s8.data_ptr() if want_s8 else None, _stream(xp)), "pq_conv2d_smallc_s8")
+    return out_f32, out_s8
+
+
 def gemm_s8(a, w, bias_q, rs, ob, hw=1, want_f32=True, want_s8=False, k_real=None, relu=False):
     """a int8 [M][K], w int8 [N][K], bias_q int32 [N] -> fp32 (NCHW with hw pixels per image,
     or [M][N] when hw == 1) and / or int8 [M][N]."""
@@ -308,16 +345,18 @@ def maxpool_nhwc_s8(x, k, stride, pad, relu=False):
     return y
 
 
-def add_requant(a, a_bit, a_relu, b, b_bit, b_relu, q_bit, want16=True, want8=True):
-    """Exact NewAdd on quantised operands (int8 or int16 tensors of identical shape)."""
+def add_requant(a, a_bit, a_relu, b, b_bit, b_relu, q_bit, want16=True, want8=True, out_relu=False):
+    """Exact NewAdd on quantised operands (int8 or int16 tensors of identical shape); out_relu fuses
+    the nn.ReLU that follows the Eltwise."""
     require_cuda(a, "add_requant")
     assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
     out16 = torch.empty(a.shape, dtype=torch.int16, device=a.device) if want16 else None
     out8 = torch.empty(a.shape, dtype=torch.int8, device=a.device) if want8 else None
     nbytes = a.numel() * (a.element_size() + b.element_size() + (2 if want16 else 0) + (1 if want8 else 0))
     with _Timed("add_requant", 1, nbytes, a.device):
-        check(lib().pq_add_requant(a.data_ptr(), 1 if a.dtype == torch.int16 else 0, int(a_bit), 1 if a_relu else 0,
-                                   b.data_ptr(), 1 if b.dtype == torch.int16 else 0, int(b_bit), 1 if b_relu else 0,
-                                   a.numel(), out16.data_ptr() if want16 else None,
-                                   out8.data_ptr() if want8 else None, int(q_bit), _stream(a)), "pq_add_requant")
+        check(lib().pq_add_requant_ex(a.data_ptr(), 1 if a.dtype == torch.int16 else 0, int(a_bit),
+                                      1 if a_relu else 0, b.data_ptr(), 1 if b.dtype == torch.int16 else 0,
+                                      int(b_bit), 1 if b_relu else 0, a.numel(), FLAG_RELU if out_relu else 0,
+                                      out16.data_ptr() if want16 else None, out8.data_ptr() if want8 else None,
+                                      int(q_bit), _stream(a)), "pq_add_requant_ex")
     return out16, out8

@@ -9,7 +9,8 @@ layers hand each other int8 NHWC payloads wrapped in a lazy ``QTensor``:
     NewConv2d -> QTensor(int8 NHWC, bit)            epilogue stores int8 (ReLU fused when it follows)
     nn.ReLU / nn.MaxPool2d on a QTensor             stay int8 (both commute with the monotone quantiser)
     NewAdd(QTensor, QTensor)                        exact integer sum: int16 (for the next identity
-                                                    shortcut) + int8 at the Eltwise's feat bit (for convs)
+                                                    shortcut) + int8 at the Eltwise's feat bit (for convs);
+                                                    evaluated lazily so that a following nn.ReLU is fused
     anything else (AvgPool2d, Concat, user code)    the QTensor de-quantises itself to fp32 NCHW first
 
 so the final output is bit-identical to the fp32-boundary model while HBM traffic drops ~4x.
@@ -26,6 +27,23 @@ _METADATA = {"__get__", "size", "dim", "numel", "element_size", "ndimension", "i
              "get_device", "is_complex", "nelement"}
 
 
+class _LazyAdd:
+    """A NewAdd whose kernel has not run yet: it runs when the first consumer asks for a payload, by
+    which time it is known whether an nn.ReLU sits between the Eltwise and that consumer."""
+
+    def __init__(self, a, abit, arelu, b, bbit, brelu, q_bit):
+        self.args = (a, abit, arelu, b, bbit, brelu, q_bit)
+        self.o_bit = max(abit, bbit)
+        self.q_bit = q_bit
+        self.done = {}                                 # relu -> (s16, q8)
+
+    def get(self, relu):
+        if relu not in self.done:
+            a, abit, arelu, b, bbit, brelu, q_bit = self.args
+            self.done[relu] = _native.add_requant(a, abit, arelu, b, bbit, brelu, q_bit, out_relu=relu)
+        return self.done[relu]
+
+
 class QTensor(torch.Tensor):
     """A float32 NCHW tensor that exists only as quantised payloads until somebody needs the floats."""
 
@@ -35,12 +53,30 @@ class QTensor(torch.Tensor):
                                                    requires_grad=False)
 
     def __init__(self, shape, device, q8=None, q8_bit=None, s16=None, s16_bit=None, relu_pending=False,
-                 nonneg=False):
-        self.q8, self.q8_bit = q8, q8_bit              # int8 NHWC, value = q8 / 2^q8_bit (after pending relu)
-        self.s16, self.s16_bit = s16, s16_bit          # int16 NHWC exact value (outputs of NewAdd)
+                 nonneg=False, lazy=None):
+        self._q8, self.q8_bit = q8, q8_bit             # int8 NHWC, value = q8 / 2^q8_bit (after pending relu)
+        self._s16, self.s16_bit = s16, s16_bit         # int16 NHWC exact value (outputs of NewAdd)
         self.relu_pending = relu_pending               # a ReLU was applied logically but not to the payloads
         self.nonneg = nonneg                           # payloads are already >= 0
+        self._lazy = lazy                              # _LazyAdd: payloads appear on first use
         self._q8_relu = None
+
+    def _materialize(self):
+        if self._lazy is not None:
+            relu = self.relu_pending
+            self._s16, self._q8 = self._lazy.get(relu)  # the pending ReLU is applied by the add kernel
+            self.nonneg = self.nonneg or relu
+            self._lazy = None
+
+    @property
+    def q8(self):
+        self._materialize()
+        return self._q8
+
+    @property
+    def s16(self):
+        self._materialize()
+        return self._s16
 
     def __repr__(self):
         return "QTensor(shape=%s, q8_bit=%s, s16_bit=%s, relu_pending=%s)" % (
@@ -49,6 +85,7 @@ class QTensor(torch.Tensor):
     # ---- payload access -------------------------------------------------------------------
     def int8_payload(self):
         """int8 NHWC with any pending ReLU applied (materialised once)."""
+        self._materialize()
         if not self.relu_pending or self.nonneg:
             return self.q8
         if self._q8_relu is None:
@@ -57,6 +94,7 @@ class QTensor(torch.Tensor):
 
     def dequantize(self):
         """fp32 NCHW, exactly what the fp32-boundary model would hold here (cold path: plain torch ops)."""
+        self._materialize()
         if self.s16 is not None:
             v = self.s16.to(torch.float32) * (2.0 ** -self.s16_bit)
         else:
@@ -68,8 +106,8 @@ class QTensor(torch.Tensor):
     def with_relu(self):
         if self.nonneg:
             return self
-        return QTensor(self.shape, self.device, q8=self.q8, q8_bit=self.q8_bit, s16=self.s16,
-                       s16_bit=self.s16_bit, relu_pending=True)
+        return QTensor(self.shape, self.device, q8=self._q8, q8_bit=self.q8_bit, s16=self._s16,
+                       s16_bit=self.s16_bit, relu_pending=True, lazy=self._lazy)
 
     # ---- dispatch -------------------------------------------------------------------------
     @classmethod
@@ -118,8 +156,9 @@ def _maxpool(x, kernel_size, stride=None, padding=0, dilation=1, ceil_mode=False
         return None
     if x.q8 is None or x.q8.shape[-1] % 16:
         return None
+    q8 = x.q8
     relu = x.relu_pending and not x.nonneg
-    y = _native.maxpool_nhwc_s8(x.q8, k[0], s[0], p[0], relu=relu)
+    y = _native.maxpool_nhwc_s8(q8, k[0], s[0], p[0], relu=relu)
     N, P, Q, C = y.shape
     return QTensor((N, x.shape[1], P, Q), x.device, q8=y, q8_bit=x.q8_bit, nonneg=x.nonneg or relu)
 
@@ -128,12 +167,16 @@ def conv_forward(mod, x):
     """NewConv2d.forward in pipeline mode."""
     conv = mod.Conv
     if isinstance(x, QTensor):
-        usable = (x.q8 is not None and x.q8_bit == mod.input_bit and not mod._explicit_im2col
-                  and x.q8.shape[-1] == mod._c_pad)
+        usable = (not mod._explicit_im2col and not getattr(mod, "_smallc", False) and x.q8 is not None
+                  and x.q8_bit == mod.input_bit and x.q8.shape[-1] == mod._c_pad)
         if not usable:
             x = x.dequantize()
     if isinstance(x, QTensor):
         q = x.int8_payload()                                     # Quantity(ib) is the identity here
+    elif getattr(mod, "_smallc", False):
+        _, out8 = mod._smallc_forward(x, want_f32=False, want_s8=True, relu=mod._fuse_relu)
+        N, P, Q, K = out8.shape
+        return QTensor((N, K, P, Q), out8.device, q8=out8, q8_bit=mod.output_bit, nonneg=mod._fuse_relu)
     elif mod._explicit_im2col:
         a, (N, P, Q) = _native.quantize_im2col_s8(x, mod.input_bit, conv.kernel_size, conv.stride,
                                                   conv.padding, mod._k_pad)
@@ -153,10 +196,11 @@ def conv_forward(mod, x):
 
 def _operand(t):
     """(payload, bit, relu) of the most exact representation of a QTensor."""
+    s16, q8 = t.s16, t.q8                              # (materialises a lazy add, fusing its ReLU)
     relu = t.relu_pending and not t.nonneg
-    if t.s16 is not None:
-        return t.s16, t.s16_bit, relu
-    return t.q8, t.q8_bit, relu
+    if s16 is not None:
+        return s16, t.s16_bit, relu
+    return q8, t.q8_bit, relu
 
 
 def add_forward(mod, x, y):
@@ -169,8 +213,8 @@ def add_forward(mod, x, y):
     if q_bit is None or a.shape != b.shape or not (0 <= o_bit <= 7) or o_bit - min(abit, bbit) > 7 \
             or abs(q_bit - o_bit) > 15:
         return None
-    s16, q8 = _native.add_requant(a, abit, arelu, b, bbit, brelu, q_bit)
-    return QTensor(x.shape, x.device, q8=q8, q8_bit=q_bit, s16=s16, s16_bit=o_bit)
+    return QTensor(x.shape, x.device, q8_bit=q_bit, s16_bit=o_bit,
+                   lazy=_LazyAdd(a, abit, arelu, b, bbit, brelu, q_bit))
 
 
 def enable_int8_pipeline(model, enabled=True):
@@ -197,3 +241,38 @@ def enable_int8_pipeline(model, enabled=True):
                     if j < len(kids) and isinstance(kids[j], nn.ReLU):
                         k._fuse_relu = True
     return model
+
+
+class GraphedForward:
+    """One captured forward of a (pipeline-enabled) ReconModel for a fixed input shape, replayed as a
+    CUDA graph: the ~90 kernel launches, tensor-map encodes and Python dispatch of a ResNet-50 forward
+    collapse into one graph launch.  The arithmetic is the captured kernels', so outputs are unchanged.
+
+        fwd = GraphedForward(model, example_batch);  y = fwd(batch)      # y is overwritten by the next call
+    """
+
+    def __init__(self, model, example, warmup=2):
+        if not example.is_cuda:
+            raise RuntimeError("GraphedForward needs a CUDA example batch: no CPU fallback")
+        self.model = model
+        self.static_in = example.detach().clone()
+        with torch.no_grad():
+            side = torch.cuda.Stream(device=example.device)
+            side.wait_stream(torch.cuda.current_stream(example.device))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):                # lazy one-time setup must not land in the capture
+                    model(self.static_in)
+            torch.cuda.current_stream(example.device).wait_stream(side)
+            torch.cuda.synchronize(example.device)
+            self.graph = torch.cuda.CUDAGraph()
+            l0 = _native.LAUNCHES["total"]
+            with torch.cuda.graph(self.graph):
+                self.static_out = model(self.static_in)
+            self.launches = _native.LAUNCHES["total"] - l0     # kernels of this library inside the graph
+
+    def __call__(self, x):
+        if x.shape != self.static_in.shape:
+            raise RuntimeError("GraphedForward was captured for shape %s" % (tuple(self.static_in.shape),))
+        self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

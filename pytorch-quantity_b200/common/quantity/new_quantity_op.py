@@ -161,8 +161,15 @@ class NewConv2d(_IntSimBase):
         K, C, R, S = wq.shape
         # im2col TMA fetches channel blocks of 32 / 64 / 128 bytes; a 1x1 stride-1 conv is a plain GEMM
         plain = (R, S) == (1, 1) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (0, 0)
-        # very few input channels (the ResNet stem): explicit im2col + GEMM instead of padding C to 32
-        self._explicit_im2col = (not plain) and C <= 8
+        # very few input channels (the ResNet stem): instead of padding C to 32, either the windowed
+        # small-channel kernel (8-byte pixels, one TMA per filter row) or explicit im2col + GEMM
+        self._smallc = (not plain) and C <= 8 and S <= 8 and conv.stride[1] % 2 == 0
+        self._explicit_im2col = (not plain) and C <= 8 and not self._smallc
+        if self._smallc:
+            w = torch.zeros((K, R, 8, 8), dtype=torch.int8, device=wq.device)       # [K][R][tap slot][channel slot]
+            w[:, :, :S, :C] = wq.permute(0, 2, 3, 1).to(torch.int8)
+            self.register_buffer("_w_krs8", w.view(K, R, 64).contiguous())
+            return
         if self._explicit_im2col:
             self._k_pad = (R * S * C + 63) // 64 * 64
             w_nk = torch.zeros((K, self._k_pad), dtype=torch.int8, device=wq.device)
@@ -179,6 +186,9 @@ class NewConv2d(_IntSimBase):
             from .int8_pipeline import conv_forward
             return conv_forward(self, input)
         conv = self.Conv
+        if getattr(self, "_smallc", False):
+            out, _ = self._smallc_forward(input, want_f32=True, want_s8=False, relu=False)
+            return out
         if self._explicit_im2col:
             a, (N, P, Q) = _native.quantize_im2col_s8(input, self.input_bit, conv.kernel_size, conv.stride,
                                                       conv.padding, self._k_pad)       # Quan + im2col
@@ -190,6 +200,22 @@ class NewConv2d(_IntSimBase):
                                    self.rs_bit, self.output_bit,
                                    c_real=conv.in_channels)      # Conv+RightShift+BiasAdd+Sp+DeQuan
         return out
+
+
+    def _smallc_forward(self, input, want_f32, want_s8, relu):
+        """Quan into a zero-padded 8-byte-pixel NHWC image, then the windowed small-channel convolution."""
+        conv = self.Conv
+        (R, S), (sh, sw), (ph, pw) = conv.kernel_size, conv.stride, conv.padding
+        H, W = input.shape[2], input.shape[3]
+        P, Q = (H + 2 * ph - R) // sh + 1, (W + 2 * pw - S) // sw + 1
+        Hp = max((P - 1) * sh + R, H + ph)
+        Hp = (Hp + sh - 1) // sh * sh
+        Wp = max((Q - 1) * sw + 8, W + pw)
+        Wp += Wp & 1
+        xp = _native.quantize_pad_nhwc8_s8(input, self.input_bit, (ph, pw), Hp, Wp)
+        return _native.conv2d_smallc_s8(xp, self._w_krs8, self._bias_i32, (H, W), (R, S), (sh, sw), (ph, pw),
+                                        self.rs_bit, self.output_bit, want_f32=want_f32, want_s8=want_s8,
+                                        c_real=conv.in_channels, relu=relu)
 
 
 class NewLinear(_IntSimBase):

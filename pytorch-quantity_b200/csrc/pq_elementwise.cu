@@ -254,6 +254,32 @@ quantize_im2col_kernel(const float *__restrict__ x, int8_t *__restrict__ a, int 
     }
 }
 
+// Input quantiser for the small-channel convolution (pq_conv2d_smallc_s8): fp32 NCHW with C <= 8 ->
+// zero-padded NHWC image with 8-byte pixels, q[n][h + ph][w + pw][c] = q(x[n][c][h][w]); everything else
+// (spatial padding, channel slots c >= C) is written as 0.  One thread per padded pixel: C coalesced fp32
+// loads along w, one coalesced 8-byte store.
+__global__ void __launch_bounds__(kEwThreads)
+quantize_pad_nhwc8_kernel(const float *__restrict__ x, uint2 *__restrict__ q, int C, int H, int W, int ph, int pw,
+                          int Hp, int Wp, size_t total, float scale)
+{
+    const size_t HW = (size_t)H * W;
+    for (size_t t = (size_t)blockIdx.x * kEwThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kEwThreads) {
+        const int wp = (int)(t % Wp);
+        const size_t r = t / Wp;
+        const int hp = (int)(r % Hp);
+        const size_t n = r / Hp;
+        const int h = hp - ph, w = wp - pw;
+        unsigned int word[2] = {0u, 0u};
+        if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) {
+            const float *src = x + (n * C * H + h) * (size_t)W + w;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < C) word[c >> 2] |= ((unsigned int)q8i(__ldg(src + c * HW), scale) & 0xffu) << ((c & 3) * 8);
+        }
+        q[t] = make_uint2(word[0], word[1]);
+    }
+}
+
 }  // namespace pq
 
 namespace {
@@ -359,5 +385,17 @@ extern "C" int pq_quantize_im2col_s8(const float *x, int8_t *a, int N, int C, in
     if (blocks > pq::kNumSMs * 8) blocks = pq::kNumSMs * 8;
     pq::quantize_im2col_kernel<<<(unsigned int)blocks, pq::kIm2colWarps * 32, smem, (cudaStream_t)stream>>>(
         x, a, C, H, W, R, S, stride_h, stride_w, pad_h, pad_w, P, Q, kp, M, ldexpf(1.0f, ib));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pq_quantize_nchw_to_padded_nhwc8_s8(const float *x, int8_t *q, int N, int C, int H, int W, int pad_h,
+                                                   int pad_w, int Hp, int Wp, int ib, pq_stream_t stream)
+{
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || pad_h < 0 || pad_w < 0 || !x || !q) return PQ_EINVAL;
+    if (C > 8 || Hp < H + pad_h || Wp < W + pad_w || ib < -126 || ib > 126) return PQ_EUNSUPPORTED;
+    if (((unsigned long long)q) & 7ull) return PQ_EALIGN;
+    const size_t total = (size_t)N * Hp * Wp;
+    pq::quantize_pad_nhwc8_kernel<<<ew_grid(total), pq::kEwThreads, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<uint2 *>(q), C, H, W, pad_h, pad_w, Hp, Wp, total, ldexpf(1.0f, ib));
     return (int)cudaGetLastError();
 }

@@ -73,6 +73,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2,
+                                            int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c, int w,
                                                    int h, int n, uint16_t off_w, uint16_t off_h)
 {
@@ -81,6 +90,32 @@ __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap *map, uint6
         " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
         : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int threads)
+{
+    asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
+}
+// sat_s8(y0) | sat_s8(y1) << 8 | sat_s8(y2) << 16 | sat_s8(y3) << 24   (two I2IP.S8.S32.SAT)
+__device__ __forceinline__ uint32_t pack4_sat_s8(int y0, int y1, int y2, int y3)
+{
+    uint32_t t, w;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(y3), "r"(y2), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(y1), "r"(y0), "r"(t));
+    return w;
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols)
 {
@@ -154,7 +189,7 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int m, int n)
 struct GemmParams {
     int M, N;                  // output rows (pixels) and columns (channels)
     int num_kb;                // K blocks of BK bytes
-    int a_im2col;              // 0: A is a 2-D [M][K] tile source; 1: im2col over NHWC
+    int a_im2col;              // 0: A is a 2-D [M][K] tile source; 1: im2col over NHWC; 2: row windows (below)
     int R, S, cblocks;         // filter taps and BK-blocks per tap (im2col mode)
     int C;                     // padded channels (bytes per pixel)
     int P, Q;                  // output height / width (im2col mode)
@@ -162,6 +197,13 @@ struct GemmParams {
     int rs, ob;                // RightShift amount, output fractional bit
     int hw;                    // pixels per image for the fp32 NCHW store (1: plain [M][N])
     int relu;                  // int8 pipeline: apply max(y, 0) in the epilogue (a following nn.ReLU)
+    int stage_s8;              // int8 output leaves through a swizzled smem tile + TMA store (N % 16 == 0)
+    // a_im2col == 2, convolutions with <= 8 input channels (the ResNet stem): the input is a zero-padded
+    // NHWC image with 8-byte pixels, so the S taps of one filter row are BK contiguous bytes and an
+    // overlapping-stride tensor map (pixel step = stride_w * 8 bytes) fetches them for a TH x TW patch of
+    // output pixels in one tiled TMA; K loop = the R filter rows.
+    int tw_shift, TW, TH;      // output patch of one tile: TH x TW = 128 pixels, TW = 1 << tw_shift
+    int tiles_p, tiles_q;      // patches per image
     const int32_t *bias;       // [N] quantised bias (already saturated to int8 range)
     float *out_f32;            // optional
     int8_t *out_s8;            // optional, [M][N]
@@ -184,13 +226,19 @@ __device__ __forceinline__ Requant make_requant(int rs, int relu)
     q.mul = rs >= 1 ? 1 : (1 << (-rs));
     return q;
 }
-__device__ __forceinline__ int requant(int acc, const Requant &q, int bias)
+// result is saturated from below (q.lo = -128, or 0 when a ReLU is fused) but NOT from above: callers
+// finish with min(., 127) or with the saturating pack
+__device__ __forceinline__ int requant_nohi(int acc, const Requant &q, int bias)
 {
     int r;
     if (q.pos) r = (acc + q.half + (acc >> 31)) >> q.sh;
     else r = max(-128, min(127, acc)) * q.mul;
     r = max(-128, min(127, r));
-    return max(q.lo, min(127, r + bias));          // q.lo = -128, or 0 when a ReLU is fused
+    return __viaddmax_s32(r, bias, q.lo);           // max(r + bias, lo) in one VIADDMNMX
+}
+__device__ __forceinline__ int requant(int acc, const Requant &q, int bias)
+{
+    return min(127, requant_nohi(acc, q, bias));
 }
 
 template <int BN, int BK, int STAGES>
@@ -198,20 +246,22 @@ struct GemmSmem {
     static constexpr int kABytes = kBM * BK;
     static constexpr int kBBytes = BN * BK;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr size_t kTotal = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + 256 /*barriers*/;
+    static constexpr int kOutBytes = kBM * BN;       // int8 output staging tile (swizzled rows of <= 128 B)
+    static constexpr size_t kTotal = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + kOutBytes + 256 /*barriers*/;
 };
 
 template <int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __maxnreg__(112)          // 18 warps x 112 registers = 63 K of the 64 K register file
 gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmParams p)
+               const __grid_constant__ CUtensorMap tmap_o, const GemmParams p)
 {
     using Cfg = GemmSmem<BN, BK, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + (size_t)STAGES * Cfg::kABytes;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * Cfg::kStageBytes);
+    uint8_t *smem_o = smem + (size_t)STAGES * Cfg::kStageBytes;          // 1024-byte aligned
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_o + Cfg::kOutBytes);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tmem_full_bar = empty_bar + STAGES;      // [2]
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2]
@@ -220,11 +270,12 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int total_tiles = ((p.M + kBM - 1) / kBM) * n_tiles;
+    const int total_tiles = (p.a_im2col == 2 ? p.M / kBM : (p.M + kBM - 1) / kBM) * n_tiles;   // mode 2: M = patches * 128
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        if (p.stage_s8) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, kEpiWarps); }
         fence_barrier_init();
@@ -243,11 +294,18 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
                 int wq = 0, hp = 0, nb = 0;
-                if (p.a_im2col) {                      // first output pixel of the tile -> input coords
+                if (p.a_im2col == 1) {                 // first output pixel of the tile -> input coords
                     nb = m0 / pq;
                     const int rem = m0 - nb * pq;
                     hp = rem / p.Q;
                     wq = rem - hp * p.Q;
+                }
+                if (p.a_im2col == 2) {                 // patch -> (image, first output row, first output column)
+                    const int mt = tile / n_tiles, per_img = p.tiles_p * p.tiles_q;
+                    nb = mt / per_img;
+                    const int rem = mt - nb * per_img;
+                    hp = (rem / p.tiles_q) * p.TH;
+                    wq = (rem % p.tiles_q) * p.TW;
                 }
                 int r = 0, s = 0, cb = 0;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -255,7 +313,10 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     mbar_expect_tx(full_bar + stage, Cfg::kStageBytes);
                     void *dst_a = smem_a + (size_t)stage * Cfg::kABytes;
                     void *dst_b = smem_b + (size_t)stage * Cfg::kBBytes;
-                    if (p.a_im2col) {
+                    if (p.a_im2col == 2) {             // filter row kb: padded input row = p * stride_h + kb
+                        tma_load_5d(&tmap_a, full_bar + stage, dst_a, 0, wq, hp + kb / p.stride_h, kb % p.stride_h, nb);
+                        tma_load_2d(&tmap_b, full_bar + stage, dst_b, kb * BK, n0);
+                    } else if (p.a_im2col) {
                         tma_load_im2col_4d(&tmap_a, full_bar + stage, dst_a, cb * BK, wq * p.stride_w - p.pad_w,
                                            hp * p.stride_h - p.pad_h, nb, (uint16_t)s, (uint16_t)r);
                         tma_load_2d(&tmap_b, full_bar + stage, dst_b, (r * p.S + s) * p.C + cb * BK, n0);
@@ -300,13 +361,27 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         constexpr int kCols = BN / 4;                  // columns per epilogue warp: 8, 16, 32 or 64
         constexpr int kChunk = kCols < 16 ? kCols : 16;
         constexpr int kChunks = kCols / kChunk;
+        constexpr int kRowBytes = BN < 128 ? BN : 128; // staging rows: sub-tiles of [128 rows][<= 128 bytes]
+        constexpr uint32_t kSwzMask = kRowBytes == 128 ? 7u : (kRowBytes == 64 ? 3u : 1u);
         const int row = quad * 32 + lane;
         const Requant rq = make_requant(p.rs, p.relu);
         const float dq = __int_as_float((127 - p.ob) << 23);        // 2^-ob, exact
+        const bool store_thread = threadIdx.x == 64;                // issues / retires the TMA stores
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN + part * kCols;
-            const int m = m0 + row;
+            const int m0 = (tile / n_tiles) * kBM, nt0 = (tile % n_tiles) * BN, n0 = nt0 + part * kCols;
+            int m = m0 + row, p_img = 0, p_row = 0, p_col = 0;
+            bool row_ok = m < p.M;
+            if (p.a_im2col == 2) {                     // tile row -> pixel of the TH x TW output patch
+                const int mt = tile / n_tiles, per_img = p.tiles_p * p.tiles_q;
+                p_img = mt / per_img;
+                const int rem = mt - p_img * per_img;
+                p_row = (rem / p.tiles_q) * p.TH;
+                p_col = (rem % p.tiles_q) * p.TW;
+                const int pr = p_row + (row >> p.tw_shift), pc = p_col + (row & (p.TW - 1));
+                row_ok = pr < p.P && pc < p.Q;
+                m = (p_img * p.P + pr) * p.Q + pc;
+            }
             float *of = nullptr;
             size_t cstride = 1;
             if (p.out_f32) {
@@ -318,14 +393,14 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     of = p.out_f32 + (size_t)m * p.N + n0;
                 }
             }
-            int8_t *o8 = p.out_s8 ? p.out_s8 + (size_t)m * p.N + n0 : nullptr;
+            int8_t *o8 = (p.out_s8 && !p.stage_s8) ? p.out_s8 + (size_t)m * p.N + n0 : nullptr;
             mbar_wait(tmem_full_bar + acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kCols);
+            uint32_t packed[kCols / 4];                // this thread's int8 results, 4 per word
 
             // process one chunk of kChunk columns held in registers
             auto emit = [&](const uint32_t (&a)[16], int c0) {
-                if (!(m < p.M && n0 + c0 < p.N)) return;
                 int y[16];
                 const bool full = n0 + c0 + kChunk <= p.N;
                 if (full && kChunk == 16) {            // bias is 64-byte aligned here: 4 x LDG.128, warp-uniform
@@ -333,44 +408,39 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int4 b4 = __ldg(bp + j);
-                        y[4 * j] = requant((int)a[4 * j], rq, b4.x); y[4 * j + 1] = requant((int)a[4 * j + 1], rq, b4.y);
-                        y[4 * j + 2] = requant((int)a[4 * j + 2], rq, b4.z); y[4 * j + 3] = requant((int)a[4 * j + 3], rq, b4.w);
+                        y[4 * j] = requant_nohi((int)a[4 * j], rq, b4.x); y[4 * j + 1] = requant_nohi((int)a[4 * j + 1], rq, b4.y);
+                        y[4 * j + 2] = requant_nohi((int)a[4 * j + 2], rq, b4.z); y[4 * j + 3] = requant_nohi((int)a[4 * j + 3], rq, b4.w);
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < kChunk; ++j)
-                        y[j] = requant((int)a[j], rq, n0 + c0 + j < p.N ? __ldg(p.bias + n0 + c0 + j) : 0);
+                        y[j] = requant_nohi((int)a[j], rq, n0 + c0 + j < p.N ? __ldg(p.bias + n0 + c0 + j) : 0);
                 }
+#pragma unroll
+                for (int j = 0; j < kChunk / 4; ++j)   // the pack saturates from above
+                    packed[c0 / 4 + j] = pack4_sat_s8(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                if (!(row_ok && n0 + c0 < p.N)) return;
                 if (of) {
                     if (p.hw > 1) {
 #pragma unroll
                         for (int j = 0; j < kChunk; ++j)
-                            if (full || n0 + c0 + j < p.N) of[(size_t)(c0 + j) * cstride] = __fmul_rn((float)y[j], dq);
+                            if (full || n0 + c0 + j < p.N) of[(size_t)(c0 + j) * cstride] = __fmul_rn((float)min(127, y[j]), dq);
                     } else if (full && (p.N & 3) == 0) {
 #pragma unroll
                         for (int j = 0; j < kChunk / 4; ++j)
                             *reinterpret_cast<float4 *>(of + c0 + 4 * j) =
-                                make_float4(__fmul_rn((float)y[4 * j], dq), __fmul_rn((float)y[4 * j + 1], dq),
-                                            __fmul_rn((float)y[4 * j + 2], dq), __fmul_rn((float)y[4 * j + 3], dq));
+                                make_float4(__fmul_rn((float)min(127, y[4 * j]), dq), __fmul_rn((float)min(127, y[4 * j + 1]), dq),
+                                            __fmul_rn((float)min(127, y[4 * j + 2]), dq), __fmul_rn((float)min(127, y[4 * j + 3]), dq));
                     } else {
 #pragma unroll
                         for (int j = 0; j < kChunk; ++j)
-                            if (full || n0 + c0 + j < p.N) of[c0 + j] = __fmul_rn((float)y[j], dq);
+                            if (full || n0 + c0 + j < p.N) of[c0 + j] = __fmul_rn((float)min(127, y[j]), dq);
                     }
                 }
-                if (o8) {
-                    if (full && kChunk == 16 && (p.N & 15) == 0) {
-                        uint32_t w[4];
+                if (o8) {                              // unstaged fall-back (N % 16 != 0): direct stores
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            w[j] = (uint32_t)(y[4 * j] & 0xff) | ((uint32_t)(y[4 * j + 1] & 0xff) << 8) |
-                                   ((uint32_t)(y[4 * j + 2] & 0xff) << 16) | ((uint32_t)(y[4 * j + 3] & 0xff) << 24);
-                        *reinterpret_cast<uint4 *>(o8 + c0) = make_uint4(w[0], w[1], w[2], w[3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < kChunk; ++j)
-                            if (full || n0 + c0 + j < p.N) o8[c0 + j] = (int8_t)y[j];
-                    }
+                    for (int j = 0; j < kChunk; ++j)
+                        if (full || n0 + c0 + j < p.N) o8[c0 + j] = (int8_t)min(127, y[j]);
                 }
             };
             auto load = [&](uint32_t (&a)[16], int c0) {
@@ -396,7 +466,42 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+            if (p.stage_s8) {
+                // int8 tile -> swizzled shared memory -> TMA store (full 128-byte lines; the TMA clips
+                // rows >= M and columns >= N).  The previous tile's store must have drained first.
+                if (store_thread) bulk_wait_read0();
+                epi_bar_sync(32 * kEpiWarps);
+                const int col0 = part * kCols;                          // byte column inside the tile
+                uint8_t *sub = smem_o + (col0 / kRowBytes) * (kBM * kRowBytes);
+                const uint32_t off = (uint32_t)(row * kRowBytes + (col0 % kRowBytes));
+                if (kCols >= 16) {
+#pragma unroll
+                    for (int j = 0; j < kCols / 16; ++j) {
+                        const uint32_t o = off + 16u * j;
+                        *reinterpret_cast<uint4 *>(sub + (o ^ (((o >> 7) & kSwzMask) << 4))) =
+                            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    }
+                } else {                                                // BN = 32: 8 bytes per thread
+                    *reinterpret_cast<uint2 *>(sub + (off ^ (((off >> 7) & kSwzMask) << 4))) =
+                        make_uint2(packed[0], packed[kCols / 4 - 1]);
+                }
+                fence_proxy_async();
+                epi_bar_sync(32 * kEpiWarps);
+                if (store_thread) {
+#pragma unroll
+                    for (int sb = 0; sb < BN / kRowBytes; ++sb)
+                        if (nt0 + sb * kRowBytes < p.N) {
+                            if (p.a_im2col == 2)
+                                tma_store_4d(&tmap_o, smem_o + sb * (kBM * kRowBytes), nt0 + sb * kRowBytes, p_col, p_row, p_img);
+                            else
+                                tma_store_2d(&tmap_o, smem_o + sb * (kBM * kRowBytes), nt0 + sb * kRowBytes, m0);
+                        }
+                    bulk_commit();
+                }
+            }
         }
+        if (p.stage_s8 && store_thread) bulk_wait_read0();
     }
     tc_fence_before();
     __syncthreads();
@@ -452,6 +557,17 @@ int encode_2d(CUtensorMap *map, const void *base, uint64_t k_bytes, uint64_t row
     return r == CUDA_SUCCESS ? PQ_OK : PQ_EUNSUPPORTED;
 }
 
+// rank-N tiled map over bytes: dims / box innermost first, strides[i] = byte pitch of dimension i + 1
+int encode_nd(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+              const cuuint32_t *box, int swizzle_bytes)
+{
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void *>(base), dims,
+                                strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(swizzle_bytes),
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PQ_OK : PQ_EUNSUPPORTED;
+}
+
 int encode_im2col(CUtensorMap *map, const void *base, const pq_conv_desc &d, int bk)
 {
     cuuint64_t dims[4] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
@@ -484,7 +600,7 @@ int num_sms()
 }
 
 template <int BN, int BK, int STAGES>
-int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, const pq::GemmParams &p, cudaStream_t s)
+int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, cudaStream_t s)
 {
     using Cfg = pq::GemmSmem<BN, BK, STAGES>;
     static_assert(Cfg::kTotal <= 227 * 1024, "shared memory budget");
@@ -496,13 +612,31 @@ int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, const pq::GemmParam
     }
     const long long tiles = (long long)((p.M + pq::kBM - 1) / pq::kBM) * ((p.N + BN - 1) / BN);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());     // persistent: one CTA per SM
-    kern<<<grid, pq::kGemmThreads, Cfg::kTotal, s>>>(ta, tb, p);
+    // int8 output tile: [128 rows][min(BN, 128) bytes] boxes of the row-major [M][N] result
+    CUtensorMap to = {};
+    p.stage_s8 = 0;
+    if (p.out_s8 && (p.N & 15) == 0 && (((uintptr_t)p.out_s8) & 15) == 0) {
+        constexpr int kRowBytes = BN < 128 ? BN : 128;
+        int rc;
+        if (p.a_im2col == 2) {                     // NHWC output addressed by (channel, q, p, image): TH x TW patches
+            const cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.Q, (cuuint64_t)p.P,
+                                        (cuuint64_t)(p.M / pq::kBM / (p.tiles_p * p.tiles_q))};
+            const cuuint64_t strides[3] = {(cuuint64_t)p.N, (cuuint64_t)p.N * p.Q, (cuuint64_t)p.N * p.Q * p.P};
+            const cuuint32_t box[4] = {(cuuint32_t)kRowBytes, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+            rc = encode_nd(&to, p.out_s8, 4, dims, strides, box, kRowBytes);
+        } else {
+            rc = encode_2d(&to, p.out_s8, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.N, kRowBytes, pq::kBM);
+        }
+        if (rc != PQ_OK) return rc;
+        p.stage_s8 = 1;
+    }
+    kern<<<grid, pq::kGemmThreads, Cfg::kTotal, s>>>(ta, tb, to, p);
     return (int)cudaGetLastError();
 }
 
 // stage counts: fill ~192 KB of shared memory, at most 8 stages
 template <int BK>
-int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, const pq::GemmParams &p, int bn, cudaStream_t s)
+int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, int bn, cudaStream_t s)
 {
     constexpr int S256 = BK == 128 ? 4 : 8;
     constexpr int S128 = BK == 128 ? 6 : 8;
@@ -524,7 +658,7 @@ int pick_bn(long long m, int n)
     return 32 < cap && m_tiles * ((n + 63) / 64) >= num_sms() ? 64 : 32;
 }
 
-int launch(const CUtensorMap &ta, const CUtensorMap &tb, const pq::GemmParams &p, int bk, int bn, cudaStream_t s)
+int launch(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, int bk, int bn, cudaStream_t s)
 {
     switch (bk) {
         case 128: return launch_bn<128>(ta, tb, p, bn, s);
@@ -607,4 +741,52 @@ extern "C" int pq_conv2d_s8_ex(const int8_t *x_nhwc, const int8_t *w_krsc, const
     p.rs = d.rs; p.ob = d.ob; p.hw = d.P * d.Q; p.bias = bias_q; p.out_f32 = out_f32_nchw; p.out_s8 = out_s8_nhwc;
     p.relu = flags & PQ_FLAG_RELU;
     return launch(ta, tb, p, bk, bn, (cudaStream_t)stream);
+}
+
+// Convolution with <= 8 input channels over a zero-padded NHWC image with 8-byte pixels (see GemmParams):
+// xp is [N][Hp][Wp][8] int8 as written by pq_quantize_nchw_to_padded_nhwc8_s8 (image pixel (h, w) at
+// (h + pad_h, w + pad_w)), w_krs8 is [K][R][64] int8: 8 pixel slots x 8 channel slots per filter row, zero
+// where s >= S or c >= C.  Requires stride_w * 8 % 16 == 0 (even stride_w), S <= 8, Hp % stride_h == 0.
+extern "C" int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const int32_t *bias_q,
+                                   const pq_conv_desc *desc_host, int Hp, int Wp, int flags, float *out_f32_nchw,
+                                   int8_t *out_s8_nhwc, pq_stream_t stream)
+{
+    if (!xp || !w_krs8 || !bias_q || !desc_host || (!out_f32_nchw && !out_s8_nhwc)) return PQ_EINVAL;
+    const pq_conv_desc &d = *desc_host;
+    if (d.N <= 0 || d.H <= 0 || d.W <= 0 || d.K <= 0 || d.R <= 0 || d.S <= 0) return PQ_EINVAL;
+    if (d.stride_h <= 0 || d.stride_w <= 0 || d.pad_h < 0 || d.pad_w < 0) return PQ_EINVAL;
+    if (d.P != (d.H + 2 * d.pad_h - d.R) / d.stride_h + 1 || d.Q != (d.W + 2 * d.pad_w - d.S) / d.stride_w + 1)
+        return PQ_EINVAL;
+    constexpr int kPix = 8, kBK = 64;
+    if (d.C != kPix || d.S > kBK / kPix || (d.stride_w & 1) || d.R > 64) return PQ_EUNSUPPORTED;
+    if (Hp % d.stride_h || Hp < (d.P - 1) * d.stride_h + d.R || Hp < d.H + d.pad_h) return PQ_EUNSUPPORTED;
+    if ((Wp * kPix) % 16 || Wp < (d.Q - 1) * d.stride_w + kBK / kPix || Wp < d.W + d.pad_w) return PQ_EUNSUPPORTED;
+    if (d.ob < -100 || d.ob > 100 || d.rs > 24 || d.rs < -24) return PQ_EUNSUPPORTED;
+    if ((((uintptr_t)xp | (uintptr_t)w_krs8 | (uintptr_t)bias_q) & 15)) return PQ_EALIGN;
+    int rc = load_driver_entry_points();
+    if (rc != PQ_OK) return rc;
+    pq::GemmParams p = {};
+    p.a_im2col = 2;
+    p.tw_shift = d.Q >= 16 ? 4 : (d.Q >= 8 ? 3 : 2);
+    p.TW = 1 << p.tw_shift; p.TH = pq::kBM / p.TW;
+    p.tiles_q = (d.Q + p.TW - 1) / p.TW; p.tiles_p = (d.P + p.TH - 1) / p.TH;
+    const long long patches = (long long)d.N * p.tiles_p * p.tiles_q;
+    if (patches * pq::kBM > 0x7fffffffLL) return PQ_EUNSUPPORTED;
+    p.M = (int)(patches * pq::kBM); p.N = d.K; p.num_kb = d.R;
+    p.R = d.R; p.S = d.S; p.C = kPix; p.P = d.P; p.Q = d.Q;
+    p.stride_h = d.stride_h; p.stride_w = d.stride_w; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
+    p.rs = d.rs; p.ob = d.ob; p.hw = d.P * d.Q; p.bias = bias_q; p.out_f32 = out_f32_nchw; p.out_s8 = out_s8_nhwc;
+    p.relu = flags & PQ_FLAG_RELU;
+    // A: (byte in window, output column, row group, row phase, image); the column step overlaps the windows
+    CUtensorMap ta, tb;
+    const cuuint64_t row_pitch = (cuuint64_t)Wp * kPix;
+    const cuuint64_t dims[5] = {(cuuint64_t)kBK, (cuuint64_t)d.Q, (cuuint64_t)(Hp / d.stride_h), (cuuint64_t)d.stride_h,
+                                (cuuint64_t)d.N};
+    const cuuint64_t strides[4] = {(cuuint64_t)d.stride_w * kPix, row_pitch * d.stride_h, row_pitch, row_pitch * Hp};
+    const cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1, 1};
+    if ((rc = encode_nd(&ta, xp, 5, dims, strides, box, kBK)) != PQ_OK) return rc;
+    const int bn = pick_bn((long long)p.M, d.K);
+    const uint64_t ktot = (uint64_t)d.R * kBK;
+    if ((rc = encode_2d(&tb, w_krs8, ktot, d.K, ktot, kBK, bn)) != PQ_OK) return rc;
+    return launch(ta, tb, p, kBK, bn, (cudaStream_t)stream);
 }

@@ -58,6 +58,7 @@ maxpool_nhwc_s8_kernel(const int8_t *__restrict__ x, int8_t *__restrict__ y, int
 struct AddParams {
     const void *a, *b;
     int a_is16, b_is16, a_relu, b_relu;
+    int out_relu;                  // a following nn.ReLU fused: s = max(s, 0)
     int a_shift, b_shift;          // o_bit - a_bit, o_bit - b_bit  (>= 0)
     int lo, hi;                    // clamp of the real sum to [-128, 127] in units of 2^-o_bit
     int q_shift;                   // q_bit - o_bit
@@ -120,7 +121,7 @@ add_requant_kernel(const AddParams p, size_t n)
             int x = av[j], y = bv[j];
             if (p.a_relu) x = max(x, 0);
             if (p.b_relu) y = max(y, 0);
-            const int num = max(p.lo, min(p.hi, (x << p.a_shift) + (y << p.b_shift)));
+            const int num = max(p.lo, min(p.hi, (x << p.a_shift) + (y << p.b_shift)));   // p.lo = 0 with a fused ReLU
             o16[j >> 1] |= ((uint32_t)num & 0xffffu) << ((j & 1) * 16);
             o8[j >> 2] |= ((uint32_t)requant_rne(num, p.q_shift) & 0xffu) << ((j & 3) * 8);
         }
@@ -177,6 +178,13 @@ extern "C" int pq_maxpool_nhwc_s8(const int8_t *x, int8_t *y, int N, int H, int 
 extern "C" int pq_add_requant(const void *a, int a_is16, int a_bit, int a_relu, const void *b, int b_is16, int b_bit,
                               int b_relu, size_t n, int16_t *out16, int8_t *out8, int q_bit, pq_stream_t stream)
 {
+    return pq_add_requant_ex(a, a_is16, a_bit, a_relu, b, b_is16, b_bit, b_relu, n, 0, out16, out8, q_bit, stream);
+}
+
+extern "C" int pq_add_requant_ex(const void *a, int a_is16, int a_bit, int a_relu, const void *b, int b_is16,
+                                 int b_bit, int b_relu, size_t n, int flags, int16_t *out16, int8_t *out8,
+                                 int q_bit, pq_stream_t stream)
+{
     if (n == 0) return PQ_OK;
     if (!a || !b || (!out16 && !out8)) return PQ_EINVAL;
     if (!al16(a) || !al16(b) || (out16 && !al16(out16)) || (out8 && !al16(out8))) return PQ_EALIGN;
@@ -186,7 +194,8 @@ extern "C" int pq_add_requant(const void *a, int a_is16, int a_bit, int a_relu, 
     pq::AddParams p;
     p.a = a; p.b = b; p.a_is16 = a_is16; p.b_is16 = b_is16; p.a_relu = a_relu; p.b_relu = b_relu;
     p.a_shift = o_bit - a_bit; p.b_shift = o_bit - b_bit;
-    p.lo = -128 * (1 << o_bit); p.hi = 127 * (1 << o_bit);
+    p.out_relu = flags & PQ_FLAG_RELU;
+    p.lo = p.out_relu ? 0 : -128 * (1 << o_bit); p.hi = 127 * (1 << o_bit);
     p.q_shift = q_bit - o_bit; p.out16 = out16; p.out8 = out8;
     pq::add_requant_kernel<<<pipe_grid((n >> 3) + 1), pq::kPipeThreads, 0, (cudaStream_t)stream>>>(p, n);
     return (int)cudaGetLastError();

@@ -1,0 +1,15 @@
+#!/bin/bash
+# gpurun wrapper: smoke, GPU tests, headline bench (+reference arm), simulation bench, per-layer conv table.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps ${STEPS:-16} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+tail -3 gpurun_out/bench.err | cut -c1-300; cat gpurun_out/bench.json
+timeout 600 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
+timeout 900 python bench_sim.py --mode both > gpurun_out/bench_sim.json 2> gpurun_out/bench_sim.err; echo "sim rc=$?"
+tail -3 gpurun_out/bench_sim.err | cut -c1-300; cat gpurun_out/bench_sim.json
+timeout 600 python bench_conv_layers.py > gpurun_out/conv_layers.txt 2>&1
+timeout 600 python bench_conv_layers.py --s8-out > gpurun_out/conv_layers_s8.txt 2>&1
+cat gpurun_out/conv_layers_s8.txt

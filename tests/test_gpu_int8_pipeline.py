@@ -40,18 +40,21 @@ def test_add_requant_exact(abit, bbit, qbit, a16, b16):
         lo = -128 * 2 ** bit if is16 else -128
         return rng.integers(lo, lim + 1, size=n).astype(np.int16 if is16 else np.int8)
     a, b = operand(a16, abit), operand(b16, bbit)
-    for arelu, brelu in ((False, False), (True, False), (True, True)):
+    for arelu, brelu, orelu in ((False, False, False), (True, False, False), (True, True, True), (False, False, True)):
         av = np.maximum(a, 0) if arelu else a
         bv = np.maximum(b, 0) if brelu else b
-        # the reference's arithmetic: fp32 sum of the real values, clamp, then the consumer's Quantity(q_bit)
+        # the reference's arithmetic: fp32 sum of the real values, clamp, [the nn.ReLU after the Eltwise,]
+        # then the consumer's Quantity(q_bit)
         s = np.clip(av.astype(np.float32) / np.float32(2 ** abit) + bv.astype(np.float32) / np.float32(2 ** bbit),
                     np.float32(-128), np.float32(127))
+        if orelu:
+            s = np.maximum(s, np.float32(0))
         o = max(abit, bbit)
         ref16 = (s * np.float32(2 ** o)).astype(np.int64)
         assert np.array_equal(ref16, s.astype(np.float64) * 2 ** o)          # exact
         ref8 = np.clip(np.rint(s * np.float32(2.0 ** qbit)), -128, 127).astype(np.int64)
         ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
-        o16, o8 = _native.add_requant(ta, abit, arelu, tb, bbit, brelu, qbit)
+        o16, o8 = _native.add_requant(ta, abit, arelu, tb, bbit, brelu, qbit, out_relu=orelu)
         assert np.array_equal(o16.cpu().numpy().astype(np.int64), ref16)
         assert np.array_equal(o8.cpu().numpy().astype(np.int64), ref8)
 
@@ -106,9 +109,17 @@ def test_pipeline_equals_fp32_boundary_model(tmp_path, model_name, batch):
                 want = torch.relu(want)          # the ReLU that follows was fused into this epilogue
             assert torch.equal(got, want), name
     assert n_q >= 15
+    # the same forward captured once and replayed as a CUDA graph, on the capture batch and on a new one
+    from common.quantity import GraphedForward
+    fwd = GraphedForward(model, x)
+    assert fwd.launches > 0
+    assert torch.equal(fwd(x), ref)
+    x2 = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(43)).cuda()
+    got2 = fwd(x2).clone()
     enable_int8_pipeline(model, False)
     with torch.no_grad():
         assert torch.equal(model(x), ref)
+        assert torch.equal(model(x2), got2)
 
 
 def test_pipeline_fallback_paths_tiny_net(tmp_path):

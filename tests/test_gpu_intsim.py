@@ -93,6 +93,67 @@ def test_conv_s8_resnet50_geometries_vs_oracle(oracle, shape):
     assert np.array_equal(y, ref)
 
 
+# small-channel ("stem") convolutions: (B, Cin, H, W, Cout, k, stride, pad) incl. ragged patches (P, Q not
+# multiples of the 8 x 16 output patch), one channel, eight channels, 3x3 and 5x5 filters
+SMALLC_SHAPES = [(2, 3, 64, 64, 64, 7, 2, 3), (3, 3, 37, 53, 32, 7, 2, 3), (1, 1, 30, 30, 16, 3, 2, 1),
+                 (2, 8, 21, 19, 48, 5, 2, 2), (2, 4, 18, 10, 256, 3, 2, 0), (1, 3, 224, 224, 64, 7, 2, 3)]
+
+
+@pytest.mark.parametrize("shape", SMALLC_SHAPES, ids=["b%d_c%d_%dx%d_o%d_k%d" % s[:6] for s in SMALLC_SHAPES])
+@pytest.mark.parametrize("relu", [False, True])
+def test_smallc_conv_vs_oracle_and_im2col(oracle, shape, relu):
+    """pq_quantize_nchw_to_padded_nhwc8_s8 + pq_conv2d_smallc_s8 (overlapping-window TMA) against the oracle's
+    integer conv layer and against the explicit-im2col GEMM path, fp32 NCHW and int8 NHWC outputs."""
+    import common.quantity as cq
+    from common.quantity import _native
+    B, Cin, H, W, Cout, k, stride, pad = shape
+    x = det_inputs.bell(B * Cin * H * W, 400 + Cin + H, 2.0).reshape(B, Cin, H, W)
+    w = det_inputs.bell(Cout * Cin * k * k, 401 + Cin, 0.05).reshape(Cout, Cin, k, k)
+    b = det_inputs.bell(Cout, 402 + Cin, 1.0)
+    info = {"weight_bit": 9, "input_bit": 5, "output_bit": 4, "bias_bit": 4}
+    conv = nn.Conv2d(Cin, Cout, k, stride=stride, padding=pad)
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(w)); conv.bias.copy_(torch.from_numpy(b))
+        m = cq.NewConv2d(conv.cuda(), dict(info))
+        assert m._smallc
+        f32, s8 = m._smallc_forward(dev(x), want_f32=True, want_s8=True, relu=relu)
+    ref, _ = oracle.int_conv_layer(x, w, b, info, stride=stride, padding=pad)
+    if relu:
+        ref = np.maximum(ref, 0)
+    assert np.array_equal(f32.cpu().numpy(), ref)
+    assert np.array_equal(s8.permute(0, 3, 1, 2).cpu().numpy().astype(np.float32) / 16.0, ref)
+    # the explicit im2col + GEMM path computes the same thing
+    kp = (k * k * Cin + 63) // 64 * 64
+    wq = m.Conv.weight.data.permute(0, 2, 3, 1).reshape(Cout, -1).to(torch.int8)
+    w_nk = torch.zeros((Cout, kp), dtype=torch.int8, device="cuda")
+    w_nk[:, :wq.shape[1]] = wq
+    a, (N, P, Q) = _native.quantize_im2col_s8(dev(x), 5, (k, k), (stride, stride), (pad, pad), kp)
+    _, s8b = _native.gemm_s8(a, w_nk, m._bias_i32, m.rs_bit, 4, hw=1, want_f32=False, want_s8=True, relu=relu)
+    assert torch.equal(s8b.view(N, P, Q, Cout), s8)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 32), (1000, 48, 64), (4099, 64, 128), (777, 128, 256), (12345, 256, 64),
+                                   (300, 512, 128), (130, 1024, 64), (64, 2048, 512), (5000, 80, 96)])
+def test_gemm_s8_staged_int8_store(oracle, M, N, K):
+    """int8 output through the swizzled shared-memory tile + TMA store (N % 16 == 0), every tile width and ragged
+    M / N edges, with and without the fused ReLU; sentinel bytes around the output must survive."""
+    from common.quantity import _native
+    rng = np.random.default_rng(M + N + K)
+    a = rng.integers(-128, 128, size=(M, K), dtype=np.int8)
+    w = rng.integers(-16, 16, size=(N, K), dtype=np.int8)
+    b = rng.integers(-128, 128, size=N).astype(np.int32)
+    acc = a.astype(np.int64) @ w.astype(np.int64).T
+    for relu in (False, True):
+        y = np.clip(oracle.right_shift(acc, 6) + b[None, :], -128, 127)
+        if relu:
+            y = np.maximum(y, 0)
+        f32, s8 = _native.gemm_s8(dev(a), dev(w), dev(b), 6, 2, want_f32=True, want_s8=True, relu=relu)
+        assert np.array_equal(s8.cpu().numpy().astype(np.int64), y)
+        assert np.array_equal(f32.cpu().numpy(), (y / 4.0).astype(np.float32))
+        _, s8_only = _native.gemm_s8(dev(a), dev(w), dev(b), 6, 2, want_f32=False, want_s8=True, relu=relu)
+        assert torch.equal(s8_only, s8)
+
+
 def test_tiny_reconmodel_bit_exact(tmp_path):
     """ReconModel of the tiny net: every NewConv2d / NewLinear / NewAdd output equals the reference's."""
     import common.quantity as cq
