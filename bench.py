@@ -130,6 +130,16 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
+    capture of this same bench command (profiles/r01_traffic.json, written by profiles/summarize.py)."""
+    try:
+        with open(os.path.join(REPO, "profiles", "r01_traffic.json")) as f:
+            return float(json.load(f)[kernel]["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_job(net, batches, n_global, workdir, rank, world):
     """One whole calibration job through the public API; returns (seconds on device, Quantity)."""
@@ -227,7 +237,7 @@ def ours(args):
     achieved = hist["avg_bytes"] / (hist["avg_ms"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "pq::hist_multi_kernel (pq_hist2048_multi_f32)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src,
+                "traffic": ncu_traffic("hist_multi"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": hist["avg_bytes"], "avg_launch_ms": round(hist["avg_ms"], 4),
                 "absmax_GBps": round(amax["avg_bytes"] / (amax["avg_ms"] * 1e-3) / 1e9, 1),
                 "kl_ms_per_job": round(kl["total_ms"], 3), "kl_us_per_tensor": round(kl["total_ms"] * 1e3 / 71, 1),

@@ -52,7 +52,17 @@ def main():
         wk[..., cin:] = 0
         bias = torch.randint(-128, 127, (cout,), dtype=torch.int32, device="cuda")
         P = (h + 2 * pad - k) // s + 1
-        if cin <= 8 and not plain:       # explicit im2col + GEMM (the stem)
+        if cin <= 8 and not plain and s % 2 == 0:      # windowed small-channel convolution (the stem)
+            w8 = torch.zeros((cout, k, 8, 8), dtype=torch.int8, device="cuda")
+            w8[:, :, :k, :cin] = torch.randint(-128, 127, (cout, k, k, cin), dtype=torch.int8, device="cuda")
+            w8 = w8.view(cout, k, 64)
+            Hp = max((P - 1) * s + k, h + pad); Hp = (Hp + s - 1) // s * s
+            Wp = max((P - 1) * s + 8, w + pad); Wp += Wp & 1
+            q = _native.quantize_pad_nhwc8_s8(x, 4, (pad, pad), Hp, Wp)
+            t_q = time_ms(lambda: _native.quantize_pad_nhwc8_s8(x, 4, (pad, pad), Hp, Wp))
+            t_c = time_ms(lambda: _native.conv2d_smallc_s8(q, w8, bias, (h, w), (k, k), (s, s), (pad, pad), 9, 4,
+                                                           want_f32=not args.s8_out, want_s8=args.s8_out))
+        elif cin <= 8 and not plain:     # explicit im2col + GEMM
             kp = (k * k * cin + 63) // 64 * 64
             wn = torch.randint(-128, 127, (cout, kp), dtype=torch.int8, device="cuda")
             wn[:, k * k * cin:] = 0

@@ -60,7 +60,15 @@ def launches(tag):
         f.write("# kernels of this repo (pq::*): %.3f ms = %.1f%% of the profiled launches\n" % (ours, 100 * ours / total))
 
 
+def _num(txt, unit):
+    v = float(txt.replace(",", ""))
+    return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
+
+
 def full(tag):
+    import json
+    traffic_path = os.path.join(REPO, "profiles", tag + "_traffic.json")
+    traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
     for rep in sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep"))):
         name = os.path.basename(rep)[5:-8]
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -76,6 +84,12 @@ def full(tag):
                         i = hdr.index(w)
                         f.write("%-92s %s %s\n" % (w, vals[i], units[i]))
                 f.write("\n")
+                ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+                traffic[name] = {"kernel": vals[hdr.index("Kernel Name")],
+                                 "dram_bytes_per_launch": _num(vals[ir], units[ir]) + _num(vals[iw], units[iw]),
+                                 "ncu_time_us": float(vals[it].replace(",", "")) * {"msecond": 1e3, "ms": 1e3, "nsecond": 1e-3, "ns": 1e-3, "second": 1e6}.get(units[it], 1.0), "source": "ncu --set full, 1 launch"}
+    with open(traffic_path, "w") as f:
+        json.dump(traffic, f, indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":

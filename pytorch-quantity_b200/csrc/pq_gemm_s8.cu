@@ -250,8 +250,206 @@ struct GemmSmem {
     static constexpr size_t kTotal = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + kOutBytes + 256 /*barriers*/;
 };
 
+
+// ---------------------------------------------------------------------------------------- epilogue
+// Executed by warps 2..17: four warps per TMEM lane quadrant, each taking a quarter of the tile's columns;
+// TMEM loads are software-pipelined against the arithmetic.  tcgen05.ld hands every lane the int32
+// accumulators of its own output row (pixel); then shift / round-half-away / saturate, + bias, saturate,
+// and either de-quantise to fp32 NCHW (the module boundary of the reference, lanes = consecutive pixels)
+// and / or pack to int8 and leave through a swizzled shared-memory tile + TMA store (full 128-byte lines;
+// the TMA clips rows >= M and columns >= N).
+template <bool POS>
+__device__ __forceinline__ int requant_t(int acc, const Requant &q, int bias)
+{
+    int r;
+    if (POS) r = (acc + q.half + (acc >> 31)) >> q.sh;        // VIADD, LEA.HI.SX32, SHF
+    else r = max(-128, min(127, acc)) * q.mul;
+    r = max(-128, min(127, r));                               // first saturation (RightShift)
+    return __viaddmax_s32(r, bias, q.lo);                     // max(r + bias, lo); callers saturate from above
+}
+
+template <int BN, bool POS, bool FAST>
+__device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap *tmap_o, uint8_t *smem_o,
+                                         uint64_t *tmem_full_bar, uint64_t *tmem_empty_bar, uint32_t tmem_base,
+                                         int total_tiles, int n_tiles)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int part = (warp - 2) >> 2;              // which quarter of the tile's columns
+    constexpr int kCols = BN / 4;                  // columns per epilogue warp: 8, 16, 32 or 64
+    constexpr int kChunk = kCols < 16 ? kCols : 16;
+    constexpr int kChunks = kCols / kChunk;
+    constexpr int kRowBytes = BN < 128 ? BN : 128; // staging rows: sub-tiles of [128 rows][<= 128 bytes]
+    constexpr uint32_t kSwzMask = kRowBytes == 128 ? 7u : (kRowBytes == 64 ? 3u : 1u);
+    const int row = quad * 32 + lane;
+    const Requant rq = make_requant(p.rs, p.relu);
+    const float dq = __int_as_float((127 - p.ob) << 23);        // 2^-ob, exact
+    const bool store_thread = threadIdx.x == 64;                // issues / retires the TMA stores
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBM, nt0 = (tile % n_tiles) * BN, n0 = nt0 + part * kCols;
+        int m = m0 + row, p_img = 0, p_row = 0, p_col = 0;
+        bool row_ok = m < p.M;
+        if (p.a_im2col == 2) {                     // tile row -> pixel of the TH x TW output patch
+            const int mt = tile / n_tiles, per_img = p.tiles_p * p.tiles_q;
+            p_img = mt / per_img;
+            const int rem = mt - p_img * per_img;
+            p_row = (rem / p.tiles_q) * p.TH;
+            p_col = (rem % p.tiles_q) * p.TW;
+            const int pr = p_row + (row >> p.tw_shift), pc = p_col + (row & (p.TW - 1));
+            row_ok = pr < p.P && pc < p.Q;
+            m = (p_img * p.P + pr) * p.Q + pc;
+        }
+        float *of = nullptr;
+        size_t cstride = 1;
+        int8_t *o8 = nullptr;
+        if (!FAST) {
+            if (p.out_f32) {
+                if (p.hw > 1) {                    // NCHW: lanes of a warp write consecutive pixels
+                    const int img = m / p.hw, pix = m - img * p.hw;
+                    of = p.out_f32 + ((size_t)img * p.N + n0) * p.hw + pix;
+                    cstride = (size_t)p.hw;
+                } else {
+                    of = p.out_f32 + (size_t)m * p.N + n0;
+                }
+            }
+            if (p.out_s8 && !p.stage_s8) o8 = p.out_s8 + (size_t)m * p.N + n0;
+        }
+        mbar_wait(tmem_full_bar + acc, acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kCols);
+        uint32_t packed[kCols / 4];                // this thread's int8 results, 4 per word
+
+        // process one chunk of kChunk columns held in registers
+        auto emit = [&](const uint32_t (&a)[16], int c0) {
+            int y[16];
+            if (FAST) {
+                // N % 16 == 0 here, so a 16-column chunk is entirely inside or outside N (outside: the TMA
+                // store clips it, nothing to compute); bias is 64-byte aligned: 4 x LDG.128, warp-uniform
+                if (kChunk == 16) {
+                    if (n0 + c0 >= p.N) return;
+                    const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int4 b4 = __ldg(bp + j);
+                        packed[c0 / 4 + j] = pack4_sat_s8(requant_t<POS>((int)a[4 * j], rq, b4.x), requant_t<POS>((int)a[4 * j + 1], rq, b4.y),
+                                                          requant_t<POS>((int)a[4 * j + 2], rq, b4.z), requant_t<POS>((int)a[4 * j + 3], rq, b4.w));
+                    }
+                } else {                           // BN = 32: 8 columns per warp; N % 16 == 0 keeps them whole too
+                    if (n0 + c0 >= p.N) return;
+                    const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
+#pragma unroll
+                    for (int j = 0; j < kChunk / 4; ++j) {
+                        const int4 b4 = __ldg(bp + j);
+                        packed[c0 / 4 + j] = pack4_sat_s8(requant_t<POS>((int)a[4 * j], rq, b4.x), requant_t<POS>((int)a[4 * j + 1], rq, b4.y),
+                                                          requant_t<POS>((int)a[4 * j + 2], rq, b4.z), requant_t<POS>((int)a[4 * j + 3], rq, b4.w));
+                    }
+                }
+                return;
+            }
+            const bool full = n0 + c0 + kChunk <= p.N;
+            if (full && kChunk == 16) {
+                const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int4 b4 = __ldg(bp + j);
+                    y[4 * j] = requant_t<POS>((int)a[4 * j], rq, b4.x); y[4 * j + 1] = requant_t<POS>((int)a[4 * j + 1], rq, b4.y);
+                    y[4 * j + 2] = requant_t<POS>((int)a[4 * j + 2], rq, b4.z); y[4 * j + 3] = requant_t<POS>((int)a[4 * j + 3], rq, b4.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j)
+                    y[j] = requant_t<POS>((int)a[j], rq, n0 + c0 + j < p.N ? __ldg(p.bias + n0 + c0 + j) : 0);
+            }
+#pragma unroll
+            for (int j = 0; j < kChunk / 4; ++j)       // the pack saturates from above
+                packed[c0 / 4 + j] = pack4_sat_s8(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+            if (!(row_ok && n0 + c0 < p.N)) return;
+            if (of) {
+                if (p.hw > 1) {
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j)
+                        if (full || n0 + c0 + j < p.N) of[(size_t)(c0 + j) * cstride] = __fmul_rn((float)min(127, y[j]), dq);
+                } else if (full && (p.N & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < kChunk / 4; ++j)
+                        *reinterpret_cast<float4 *>(of + c0 + 4 * j) =
+                            make_float4(__fmul_rn((float)min(127, y[4 * j]), dq), __fmul_rn((float)min(127, y[4 * j + 1]), dq),
+                                        __fmul_rn((float)min(127, y[4 * j + 2]), dq), __fmul_rn((float)min(127, y[4 * j + 3]), dq));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j)
+                        if (full || n0 + c0 + j < p.N) of[c0 + j] = __fmul_rn((float)min(127, y[j]), dq);
+                }
+            }
+            if (o8) {                                  // unstaged fall-back (N % 16 != 0): direct stores
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j)
+                    if (full || n0 + c0 + j < p.N) o8[c0 + j] = (int8_t)min(127, y[j]);
+            }
+        };
+        auto load = [&](uint32_t (&a)[16], int c0) {
+            if (kChunk == 16) tmem_ld16(taddr + (uint32_t)c0, a); else tmem_ld8(taddr + (uint32_t)c0, a);
+        };
+
+        // software pipeline: the TMEM load of chunk i+1 is in flight while chunk i is processed
+        uint32_t a0[16], a1[16];
+        load(a0, 0);
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ch += 2) {
+            tmem_ld_wait();
+            if (ch + 1 < kChunks) load(a1, (ch + 1) * kChunk);
+            emit(a0, ch * kChunk);
+            if (ch + 1 < kChunks) {
+                tmem_ld_wait();
+                if (ch + 2 < kChunks) load(a0, (ch + 2) * kChunk);
+                emit(a1, (ch + 1) * kChunk);
+            }
+        }
+        // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+        if (FAST || p.stage_s8) {
+            // The previous tile's TMA store must have finished reading the staging tile.
+            if (store_thread) bulk_wait_read0();
+            epi_bar_sync(32 * kEpiWarps);
+            const int col0 = part * kCols;                          // byte column inside the tile
+            uint8_t *sub = smem_o + (col0 / kRowBytes) * (kBM * kRowBytes);
+            const uint32_t off = (uint32_t)(row * kRowBytes + (col0 % kRowBytes));
+            if (kCols >= 16) {
+#pragma unroll
+                for (int j = 0; j < kCols / 16; ++j) {
+                    const uint32_t o = off + 16u * j;
+                    *reinterpret_cast<uint4 *>(sub + (o ^ (((o >> 7) & kSwzMask) << 4))) =
+                        make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                }
+            } else {                                                // BN = 32: 8 bytes per thread
+                *reinterpret_cast<uint2 *>(sub + (off ^ (((off >> 7) & kSwzMask) << 4))) =
+                    make_uint2(packed[0], packed[kCols / 4 - 1]);
+            }
+            fence_proxy_async();
+            epi_bar_sync(32 * kEpiWarps);
+            if (store_thread) {
+#pragma unroll
+                for (int sb = 0; sb < BN / kRowBytes; ++sb)
+                    if (nt0 + sb * kRowBytes < p.N) {
+                        if (p.a_im2col == 2)
+                            tma_store_4d(tmap_o, smem_o + sb * (kBM * kRowBytes), nt0 + sb * kRowBytes, p_col, p_row, p_img);
+                        else
+                            tma_store_2d(tmap_o, smem_o + sb * (kBM * kRowBytes), nt0 + sb * kRowBytes, m0);
+                    }
+                bulk_commit();
+            }
+        }
+    }
+    if ((FAST || p.stage_s8) && store_thread) bulk_wait_read0();
+}
+
 template <int BN, int BK, int STAGES>
-__global__ void __maxnreg__(112)          // 18 warps x 112 registers = 63 K of the 64 K register file
+__global__ void __launch_bounds__(kGemmThreads, 1)     // 18 warps = 5 on one SM sub-partition: 96 registers / thread
 gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const GemmParams p)
 {
@@ -356,152 +554,16 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else {
         // ===================== epilogue (warps 2..17) =====================
-        const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
-        const int part = (warp - 2) >> 2;              // which quarter of the tile's columns
-        constexpr int kCols = BN / 4;                  // columns per epilogue warp: 8, 16, 32 or 64
-        constexpr int kChunk = kCols < 16 ? kCols : 16;
-        constexpr int kChunks = kCols / kChunk;
-        constexpr int kRowBytes = BN < 128 ? BN : 128; // staging rows: sub-tiles of [128 rows][<= 128 bytes]
-        constexpr uint32_t kSwzMask = kRowBytes == 128 ? 7u : (kRowBytes == 64 ? 3u : 1u);
-        const int row = quad * 32 + lane;
-        const Requant rq = make_requant(p.rs, p.relu);
-        const float dq = __int_as_float((127 - p.ob) << 23);        // 2^-ob, exact
-        const bool store_thread = threadIdx.x == 64;                // issues / retires the TMA stores
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * kBM, nt0 = (tile % n_tiles) * BN, n0 = nt0 + part * kCols;
-            int m = m0 + row, p_img = 0, p_row = 0, p_col = 0;
-            bool row_ok = m < p.M;
-            if (p.a_im2col == 2) {                     // tile row -> pixel of the TH x TW output patch
-                const int mt = tile / n_tiles, per_img = p.tiles_p * p.tiles_q;
-                p_img = mt / per_img;
-                const int rem = mt - p_img * per_img;
-                p_row = (rem / p.tiles_q) * p.TH;
-                p_col = (rem % p.tiles_q) * p.TW;
-                const int pr = p_row + (row >> p.tw_shift), pc = p_col + (row & (p.TW - 1));
-                row_ok = pr < p.P && pc < p.Q;
-                m = (p_img * p.P + pr) * p.Q + pc;
-            }
-            float *of = nullptr;
-            size_t cstride = 1;
-            if (p.out_f32) {
-                if (p.hw > 1) {                        // NCHW: lanes of a warp write consecutive pixels
-                    const int img = m / p.hw, pix = m - img * p.hw;
-                    of = p.out_f32 + ((size_t)img * p.N + n0) * p.hw + pix;
-                    cstride = (size_t)p.hw;
-                } else {
-                    of = p.out_f32 + (size_t)m * p.N + n0;
-                }
-            }
-            int8_t *o8 = (p.out_s8 && !p.stage_s8) ? p.out_s8 + (size_t)m * p.N + n0 : nullptr;
-            mbar_wait(tmem_full_bar + acc, acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kCols);
-            uint32_t packed[kCols / 4];                // this thread's int8 results, 4 per word
-
-            // process one chunk of kChunk columns held in registers
-            auto emit = [&](const uint32_t (&a)[16], int c0) {
-                int y[16];
-                const bool full = n0 + c0 + kChunk <= p.N;
-                if (full && kChunk == 16) {            // bias is 64-byte aligned here: 4 x LDG.128, warp-uniform
-                    const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int4 b4 = __ldg(bp + j);
-                        y[4 * j] = requant_nohi((int)a[4 * j], rq, b4.x); y[4 * j + 1] = requant_nohi((int)a[4 * j + 1], rq, b4.y);
-                        y[4 * j + 2] = requant_nohi((int)a[4 * j + 2], rq, b4.z); y[4 * j + 3] = requant_nohi((int)a[4 * j + 3], rq, b4.w);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j)
-                        y[j] = requant_nohi((int)a[j], rq, n0 + c0 + j < p.N ? __ldg(p.bias + n0 + c0 + j) : 0);
-                }
-#pragma unroll
-                for (int j = 0; j < kChunk / 4; ++j)   // the pack saturates from above
-                    packed[c0 / 4 + j] = pack4_sat_s8(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-                if (!(row_ok && n0 + c0 < p.N)) return;
-                if (of) {
-                    if (p.hw > 1) {
-#pragma unroll
-                        for (int j = 0; j < kChunk; ++j)
-                            if (full || n0 + c0 + j < p.N) of[(size_t)(c0 + j) * cstride] = __fmul_rn((float)min(127, y[j]), dq);
-                    } else if (full && (p.N & 3) == 0) {
-#pragma unroll
-                        for (int j = 0; j < kChunk / 4; ++j)
-                            *reinterpret_cast<float4 *>(of + c0 + 4 * j) =
-                                make_float4(__fmul_rn((float)min(127, y[4 * j]), dq), __fmul_rn((float)min(127, y[4 * j + 1]), dq),
-                                            __fmul_rn((float)min(127, y[4 * j + 2]), dq), __fmul_rn((float)min(127, y[4 * j + 3]), dq));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < kChunk; ++j)
-                            if (full || n0 + c0 + j < p.N) of[c0 + j] = __fmul_rn((float)min(127, y[j]), dq);
-                    }
-                }
-                if (o8) {                              // unstaged fall-back (N % 16 != 0): direct stores
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j)
-                        if (full || n0 + c0 + j < p.N) o8[c0 + j] = (int8_t)min(127, y[j]);
-                }
-            };
-            auto load = [&](uint32_t (&a)[16], int c0) {
-                if (kChunk == 16) tmem_ld16(taddr + (uint32_t)c0, a); else tmem_ld8(taddr + (uint32_t)c0, a);
-            };
-
-            // software pipeline: the TMEM load of chunk i+1 is in flight while chunk i is processed
-            uint32_t a0[16], a1[16];
-            load(a0, 0);
-#pragma unroll
-            for (int ch = 0; ch < kChunks; ch += 2) {
-                tmem_ld_wait();
-                if (ch + 1 < kChunks) load(a1, (ch + 1) * kChunk);
-                emit(a0, ch * kChunk);
-                if (ch + 1 < kChunks) {
-                    tmem_ld_wait();
-                    if (ch + 2 < kChunks) load(a0, (ch + 2) * kChunk);
-                    emit(a1, (ch + 1) * kChunk);
-                }
-            }
-            // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-
-            if (p.stage_s8) {
-                // int8 tile -> swizzled shared memory -> TMA store (full 128-byte lines; the TMA clips
-                // rows >= M and columns >= N).  The previous tile's store must have drained first.
-                if (store_thread) bulk_wait_read0();
-                epi_bar_sync(32 * kEpiWarps);
-                const int col0 = part * kCols;                          // byte column inside the tile
-                uint8_t *sub = smem_o + (col0 / kRowBytes) * (kBM * kRowBytes);
-                const uint32_t off = (uint32_t)(row * kRowBytes + (col0 % kRowBytes));
-                if (kCols >= 16) {
-#pragma unroll
-                    for (int j = 0; j < kCols / 16; ++j) {
-                        const uint32_t o = off + 16u * j;
-                        *reinterpret_cast<uint4 *>(sub + (o ^ (((o >> 7) & kSwzMask) << 4))) =
-                            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                    }
-                } else {                                                // BN = 32: 8 bytes per thread
-                    *reinterpret_cast<uint2 *>(sub + (off ^ (((off >> 7) & kSwzMask) << 4))) =
-                        make_uint2(packed[0], packed[kCols / 4 - 1]);
-                }
-                fence_proxy_async();
-                epi_bar_sync(32 * kEpiWarps);
-                if (store_thread) {
-#pragma unroll
-                    for (int sb = 0; sb < BN / kRowBytes; ++sb)
-                        if (nt0 + sb * kRowBytes < p.N) {
-                            if (p.a_im2col == 2)
-                                tma_store_4d(&tmap_o, smem_o + sb * (kBM * kRowBytes), nt0 + sb * kRowBytes, p_col, p_row, p_img);
-                            else
-                                tma_store_2d(&tmap_o, smem_o + sb * (kBM * kRowBytes), nt0 + sb * kRowBytes, m0);
-                        }
-                    bulk_commit();
-                }
-            }
+        // compile-time variants: POS = right shift by rs >= 1 (the usual case), FAST = int8 output only,
+        // leaving through the staged TMA store (the int8 pipeline); anything else takes the generic body
+        const bool fast = p.stage_s8 && !p.out_f32;
+        if (p.rs >= 1) {
+            if (fast) epilogue<BN, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else epilogue<BN, true, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+        } else {
+            if (fast) epilogue<BN, false, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else epilogue<BN, false, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
         }
-        if (p.stage_s8 && store_thread) bulk_wait_read0();
     }
     tc_fence_before();
     __syncthreads();

@@ -84,40 +84,51 @@ __device__ __forceinline__ int requant_rne(int num, int sh)
     return max(-128, min(127, r));
 }
 
+__device__ __forceinline__ uint4 ld_nc_u4(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// 16 consecutive operands of vector index v, sign-extended
+template <bool IS16>
+__device__ __forceinline__ void add_load16(const void *base, size_t v, int (&out)[16])
+{
+    if (IS16) {
+        const uint4 w0 = ld_nc_u4(reinterpret_cast<const uint4 *>(base) + 2 * v);
+        const uint4 w1 = ld_nc_u4(reinterpret_cast<const uint4 *>(base) + 2 * v + 1);
+        const uint32_t ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            out[2 * j] = (int)(int16_t)(ww[j] & 0xffff);
+            out[2 * j + 1] = (int)ww[j] >> 16;
+        }
+    } else {
+        const uint4 w = ld_nc_u4(reinterpret_cast<const uint4 *>(base) + v);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) out[j] = (int)(int8_t)((ww[j >> 2] >> ((j & 3) * 8)) & 0xff);
+    }
+}
+
+// 16 elements per thread and iteration: 16 / 32-byte vector loads per operand, two 16-byte stores for the
+// int16 sum and one for the int8 requantisation (buffers are 16-byte aligned; scalar tail below)
+template <bool A16, bool B16>
 __global__ void __launch_bounds__(kPipeThreads)
 add_requant_kernel(const AddParams p, size_t n)
 {
-    // 8 elements per thread: 8-byte / 16-byte vector accesses (buffers are 16-byte aligned, n % 8 == 0
-    // handled by the scalar tail below)
-    const size_t nvec = n >> 3;
+    const size_t nvec = n >> 4;
     const size_t stride = (size_t)gridDim.x * kPipeThreads;
     for (size_t v = (size_t)blockIdx.x * kPipeThreads + threadIdx.x; v < nvec; v += stride) {
-        int av[8], bv[8];
-        if (p.a_is16) {
-            const uint4 w = reinterpret_cast<const uint4 *>(p.a)[v];
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        int av[16], bv[16];
+        add_load16<A16>(p.a, v, av);
+        add_load16<B16>(p.b, v, bv);
+        uint32_t o16[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o8[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { av[2 * j] = (int)(int16_t)(ww[j] & 0xffff); av[2 * j + 1] = (int)(int16_t)(ww[j] >> 16); }
-        } else {
-            const uint2 w = reinterpret_cast<const uint2 *>(p.a)[v];
-            const uint32_t ww[2] = {w.x, w.y};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) av[j] = (int)(int8_t)((ww[j >> 2] >> ((j & 3) * 8)) & 0xff);
-        }
-        if (p.b_is16) {
-            const uint4 w = reinterpret_cast<const uint4 *>(p.b)[v];
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { bv[2 * j] = (int)(int16_t)(ww[j] & 0xffff); bv[2 * j + 1] = (int)(int16_t)(ww[j] >> 16); }
-        } else {
-            const uint2 w = reinterpret_cast<const uint2 *>(p.b)[v];
-            const uint32_t ww[2] = {w.x, w.y};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bv[j] = (int)(int8_t)((ww[j >> 2] >> ((j & 3) * 8)) & 0xff);
-        }
-        uint32_t o16[4] = {0, 0, 0, 0}, o8[2] = {0, 0};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 16; ++j) {
             int x = av[j], y = bv[j];
             if (p.a_relu) x = max(x, 0);
             if (p.b_relu) y = max(y, 0);
@@ -125,12 +136,15 @@ add_requant_kernel(const AddParams p, size_t n)
             o16[j >> 1] |= ((uint32_t)num & 0xffffu) << ((j & 1) * 16);
             o8[j >> 2] |= ((uint32_t)requant_rne(num, p.q_shift) & 0xffu) << ((j & 3) * 8);
         }
-        if (p.out16) reinterpret_cast<uint4 *>(p.out16)[v] = make_uint4(o16[0], o16[1], o16[2], o16[3]);
-        if (p.out8) reinterpret_cast<uint2 *>(p.out8)[v] = make_uint2(o8[0], o8[1]);
+        if (p.out16) {
+            reinterpret_cast<uint4 *>(p.out16)[2 * v] = make_uint4(o16[0], o16[1], o16[2], o16[3]);
+            reinterpret_cast<uint4 *>(p.out16)[2 * v + 1] = make_uint4(o16[4], o16[5], o16[6], o16[7]);
+        }
+        if (p.out8) reinterpret_cast<uint4 *>(p.out8)[v] = make_uint4(o8[0], o8[1], o8[2], o8[3]);
     }
-    const size_t t = (nvec << 3) + (size_t)blockIdx.x * kPipeThreads + threadIdx.x;
+    const size_t t = (nvec << 4) + (size_t)blockIdx.x * kPipeThreads + threadIdx.x;
     if (t < n) {
-        int x = add_load(p.a, p.a_is16, t), y = add_load(p.b, p.b_is16, t);
+        int x = add_load(p.a, A16, t), y = add_load(p.b, B16, t);
         if (p.a_relu) x = max(x, 0);
         if (p.b_relu) y = max(y, 0);
         const int num = max(p.lo, min(p.hi, (x << p.a_shift) + (y << p.b_shift)));
@@ -197,6 +211,11 @@ extern "C" int pq_add_requant_ex(const void *a, int a_is16, int a_bit, int a_rel
     p.out_relu = flags & PQ_FLAG_RELU;
     p.lo = p.out_relu ? 0 : -128 * (1 << o_bit); p.hi = 127 * (1 << o_bit);
     p.q_shift = q_bit - o_bit; p.out16 = out16; p.out8 = out8;
-    pq::add_requant_kernel<<<pipe_grid((n >> 3) + 1), pq::kPipeThreads, 0, (cudaStream_t)stream>>>(p, n);
+    const unsigned int grid = pipe_grid((n >> 4) + 16);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a_is16 && b_is16) pq::add_requant_kernel<true, true><<<grid, pq::kPipeThreads, 0, s>>>(p, n);
+    else if (a_is16) pq::add_requant_kernel<true, false><<<grid, pq::kPipeThreads, 0, s>>>(p, n);
+    else if (b_is16) pq::add_requant_kernel<false, true><<<grid, pq::kPipeThreads, 0, s>>>(p, n);
+    else pq::add_requant_kernel<false, false><<<grid, pq::kPipeThreads, 0, s>>>(p, n);
     return (int)cudaGetLastError();
 }

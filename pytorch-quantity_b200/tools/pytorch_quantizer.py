@@ -190,9 +190,52 @@ class Quantity(object):
         img = self.preprocess(image_path)
         if not img.is_cuda:
             img = img.to(self.cuda_device, non_blocking=True)
+        self._forward_device(net, img)
+
+    def _forward_device(self, net, img):
         self._begin_forward()
         with torch.no_grad():
             net(img)
+
+    def _device_batches(self, images_files, skip=None):
+        """This rank's batches as device tensors, ``(index, tensor or None)``: the host->device copy of
+        batch i+1 is issued on a copy stream while batch i is being processed (pinned host batches
+        overlap completely).  ``skip(index)`` true: nothing is copied and None is yielded."""
+        dev = self.cuda_device
+        copy_stream = None
+
+        def stage(item):
+            nonlocal copy_stream
+            i, image = item
+            if skip is not None and skip(i):
+                return i, None, None
+            img = self.preprocess(image)
+            if img.is_cuda:
+                return i, img, None
+            if copy_stream is None:
+                copy_stream = torch.cuda.Stream(dev)
+            with torch.cuda.stream(copy_stream):
+                staged = img.to(dev, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            return i, staged, done
+
+        pending = None
+        for item in self._my_batches(images_files):
+            ahead = stage(item)
+            if pending is not None:
+                yield self._claim(pending)
+            pending = ahead
+        if pending is not None:
+            yield self._claim(pending)
+
+    def _claim(self, staged):
+        i, img, done = staged
+        if done is not None:
+            cur = torch.cuda.current_stream(self.cuda_device)
+            cur.wait_event(done)
+            img.record_stream(cur)
+        return i, img
 
     # --------------------------------------------------------------- activation hooks
     def regist_hook_outfeature(self, model):
@@ -254,8 +297,8 @@ class Quantity(object):
 
         t0 = time.perf_counter()
         n_mine = 0
-        for i, image in self._my_batches(images_files):                      # pass 1  (:379-390)
-            self.net_forward(self.model, image)
+        for i, img in self._device_batches(images_files):                    # pass 1  (:379-390)
+            self._forward_device(self.model, img)
             feats = {n: named_feats[n] for n in top_feat_names}
             collector.refresh_max_val(feats)
             nbytes = sum(t.numel() * t.element_size() for t in feats.values())
@@ -285,11 +328,11 @@ class Quantity(object):
                 distribution_intervals[n] = widest
 
         self._log("Collect histograms of activations:")
-        for i, image in self._my_batches(images_files):                      # pass 2  (:415-426)
-            if i in cache:
+        for i, img in self._device_batches(images_files, skip=lambda i: i in cache):   # pass 2  (:415-426)
+            if img is None:
                 feats = cache.pop(i)
             else:
-                self.net_forward(self.model, image)
+                self._forward_device(self.model, img)
                 feats = {n: named_feats[n] for n in top_feat_names}
             collector.add_to_distributions(feats)
         if n_mine == 0:

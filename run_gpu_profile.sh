@@ -12,7 +12,7 @@ for K in hist_multi absmax_multi kl_candidate; do
   echo "$K rc=$?"
 done
 # fake-quant is not on the calibration path: profile it from the GPU test that runs it at C2 scale
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fakequant_kernel -s 8 -c 1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fakequant_kernel -s 0 -c 1 \
     -f -o gpurun_out/prof_fakequant python -m pytest tests/test_gpu_parity.py -q -m gpu -k "fakequant_full_size" > gpurun_out/ncu_fakequant.log 2>&1
 echo "fakequant rc=$?"
 # int8 tensor-core kernel: one compute-bound 3x3 layer (row 16) and one store-bound 1x1 layer (row 3), int8 output
