@@ -73,6 +73,13 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2,
                                             int c3, int c4)
 {
@@ -570,6 +577,130 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ------------------------------------------------------------------------ small-channel "row" kernel
+// Convolutions with <= 8 input channels, stride_w == 2 and S <= 8 (the ResNet stem) over the zero-padded
+// 8-byte-pixel NHWC image.  One tile = 128 consecutive output columns of ONE output row; its A operand for
+// filter row r is the padded input row p*stride_h + r itself: output column q reads the 64 bytes that
+// start 16*q bytes into that row, so consecutive GEMM rows are 16 bytes apart -- exactly the row pitch of
+// an un-swizzled K-major core matrix.  A shared-memory descriptor with LBO = 16 B (next 16-byte K chunk)
+// and SBO = 128 B (next 8 rows) therefore lets the tensor core read the overlapping windows straight out
+// of the raw rows: per tile ONE contiguous bulk copy of R input rows (12.9 KB for the 7x7 stem) replaces
+// 7 x 128 window fetches (56 KB), and the weights stay resident in shared memory for the whole kernel.
+struct RowsParams {
+    const int8_t *xp;          // [N][Hp][pitch] bytes
+    int pitch, Hp;             // bytes per padded row, padded rows per image
+    int a_stage, stages;       // bytes per A ring slot (R rows + over-read slack), ring depth
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_interleave(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);          // start address
+    d |= (uint64_t)(16 >> 4) << 16;                      // LBO: next 16-byte chunk along K
+    d |= (uint64_t)(128 >> 4) << 32;                     // SBO: next group of 8 rows
+    d |= (uint64_t)1 << 46;                              // descriptor version (layout type 0 = no swizzle)
+    return d;
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o,
+                    const GemmParams p, const RowsParams rp)
+{
+    constexpr int BN = 64, BK = 64, kMaxStages = 8;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int n_tiles = (p.N + BN - 1) / BN;
+    uint8_t *smem_b = smem;                                              // [n_tiles][R][64 filters][64 B], 64B swizzle
+    uint8_t *smem_o = smem_b + (size_t)n_tiles * p.R * (BN * BK);       // 8 KB, 1024-byte aligned
+    uint8_t *smem_a = smem_o + kBM * BN;                                 // ring of raw input rows
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_a + (size_t)rp.stages * rp.a_stage);
+    uint64_t *empty_bar = full_bar + kMaxStages;
+    uint64_t *tmem_full_bar = empty_bar + kMaxStages;
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;
+    uint64_t *b_bar = tmem_empty_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = 2 * BN;
+    const int total_tiles = (p.M / kBM) * n_tiles;
+    const int per_img = p.tiles_p * p.tiles_q;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
+        for (int s = 0; s < rp.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, kEpiWarps); }
+        mbar_init(b_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // weights: resident for the whole kernel
+            mbar_expect_tx(b_bar, (uint32_t)(n_tiles * p.R * BN * BK));
+            for (int nt = 0; nt < n_tiles; ++nt)
+                for (int r = 0; r < p.R; ++r)
+                    tma_load_2d(&tmap_b, b_bar, smem_b + (size_t)(nt * p.R + r) * (BN * BK), r * BK, nt * BN);
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t bytes = (uint32_t)(p.R * rp.pitch);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / n_tiles;
+                const int img = mt / per_img, prow = (mt - img * per_img) / p.tiles_q;
+                mbar_wait(empty_bar + stage, phase ^ 1);
+                mbar_expect_tx(full_bar + stage, bytes);
+                bulk_load_1d(smem_a + (size_t)stage * rp.a_stage,
+                             rp.xp + ((size_t)img * rp.Hp + (size_t)prow * p.stride_h) * rp.pitch, bytes, full_bar + stage);
+                if (++stage == rp.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_i8(kBM, BN);
+            mbar_wait(b_bar, 0);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+                const int q0 = ((mt % per_img) % p.tiles_q) * kBM;
+                mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
+                mbar_wait(full_bar + stage, phase);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t a0 = smem_u32(smem_a + (size_t)stage * rp.a_stage) + (uint32_t)(q0 * 16);
+                const uint32_t b0 = smem_u32(smem_b + (size_t)nt * p.R * (BN * BK));
+                for (int r = 0; r < p.R; ++r) {
+                    const uint64_t db = make_smem_desc<BK>(b0 + (uint32_t)(r * BN * BK));
+#pragma unroll
+                    for (int k = 0; k < BK / 32; ++k)
+                        umma_i8(tmem_d, make_smem_desc_interleave(a0 + (uint32_t)(r * rp.pitch + k * 32)),
+                                db + (uint64_t)(2 * k), idesc, (r | k) != 0);
+                }
+                umma_commit(empty_bar + stage);
+                umma_commit(tmem_full_bar + acc);
+                if (++stage == rp.stages) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const bool fast = p.stage_s8 && !p.out_f32;
+        if (p.rs >= 1) {
+            if (fast) epilogue<BN, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else epilogue<BN, true, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+        } else {
+            if (fast) epilogue<BN, false, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else epilogue<BN, false, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 }  // namespace pq
 
 // ------------------------------------------------------------------------------------ host side
@@ -839,6 +970,46 @@ extern "C" int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const
     p.stride_h = d.stride_h; p.stride_w = d.stride_w; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
     p.rs = d.rs; p.ob = d.ob; p.hw = d.P * d.Q; p.bias = bias_q; p.out_f32 = out_f32_nchw; p.out_s8 = out_s8_nhwc;
     p.relu = flags & PQ_FLAG_RELU;
+    // Preferred: the row kernel (stride_w == 2: GEMM rows 16 bytes apart == an un-swizzled core matrix)
+    if (d.stride_w == 2 && d.R <= 8) {
+        const int n_tiles = (d.K + 63) / 64;
+        const int pitch = Wp * kPix;
+        const int tiles_q = (d.Q + pq::kBM - 1) / pq::kBM;
+        const int a_stage = (d.R * pitch + 2112 + 1023) / 1024 * 1024;       // + over-read of the last window rows
+        const long long fixed = 1024 + (long long)n_tiles * d.R * 4096 + pq::kBM * 64 + 256;
+        const long long stages_fit = (227 * 1024 - fixed) / a_stage;
+        const long long tiles_m = (long long)d.N * d.P * tiles_q;
+        if (stages_fit >= 2 && tiles_m * pq::kBM <= 0x7fffffffLL &&
+            (long long)(d.R - 1) * pitch + (long long)(tiles_q * pq::kBM - 1) * 16 + 64 <= a_stage) {
+            pq::RowsParams rp;
+            rp.xp = xp; rp.pitch = pitch; rp.Hp = Hp; rp.a_stage = a_stage;
+            rp.stages = (int)(stages_fit < 8 ? stages_fit : 8);
+            pq::GemmParams q = p;
+            q.tw_shift = 7; q.TW = pq::kBM; q.TH = 1; q.tiles_q = tiles_q; q.tiles_p = d.P;
+            q.M = (int)(tiles_m * pq::kBM);
+            CUtensorMap tb, to = {};
+            const uint64_t ktot = (uint64_t)d.R * kBK;
+            if ((rc = encode_2d(&tb, w_krs8, ktot, d.K, ktot, kBK, 64)) != PQ_OK) return rc;
+            q.stage_s8 = 0;
+            if (q.out_s8 && (q.N & 15) == 0 && (((uintptr_t)q.out_s8) & 15) == 0) {
+                const cuuint64_t odims[4] = {(cuuint64_t)q.N, (cuuint64_t)q.Q, (cuuint64_t)q.P, (cuuint64_t)d.N};
+                const cuuint64_t ostr[3] = {(cuuint64_t)q.N, (cuuint64_t)q.N * q.Q, (cuuint64_t)q.N * q.Q * q.P};
+                const cuuint32_t obox[4] = {64, (cuuint32_t)q.TW, 1, 1};
+                if ((rc = encode_nd(&to, q.out_s8, 4, odims, ostr, obox, 64)) != PQ_OK) return rc;
+                q.stage_s8 = 1;
+            }
+            const size_t smem = (size_t)fixed + (size_t)rp.stages * a_stage;
+            static size_t attr = 0;
+            if (smem > attr) {
+                PQ_CUDA_TRY(cudaFuncSetAttribute(pq::conv_rows_s8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr = smem;
+            }
+            const long long tiles = tiles_m * n_tiles;
+            const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+            pq::conv_rows_s8_kernel<<<grid, pq::kGemmThreads, smem, (cudaStream_t)stream>>>(tb, to, q, rp);
+            return (int)cudaGetLastError();
+        }
+    }
     // A: (byte in window, output column, row group, row phase, image); the column step overlaps the windows
     CUtensorMap ta, tb;
     const cuuint64_t row_pitch = (cuuint64_t)Wp * kPix;

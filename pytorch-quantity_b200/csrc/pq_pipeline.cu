@@ -93,7 +93,16 @@ __device__ __forceinline__ uint4 ld_nc_u4(const uint4 *p)
     return r;
 }
 
-// 16 consecutive operands of vector index v, sign-extended
+// byte permute with sign replication (selector nibble bit 3): one instruction sign-extends a packed
+// int8 / int16 lane to 32 bits
+__device__ __forceinline__ int prmt_sx(uint32_t w, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0u), "r"(sel));
+    return (int)d;
+}
+
+// 16 consecutive operands of vector index v, sign-extended (one PRMT each)
 template <bool IS16>
 __device__ __forceinline__ void add_load16(const void *base, size_t v, int (&out)[16])
 {
@@ -103,44 +112,70 @@ __device__ __forceinline__ void add_load16(const void *base, size_t v, int (&out
         const uint32_t ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            out[2 * j] = (int)(int16_t)(ww[j] & 0xffff);
-            out[2 * j + 1] = (int)ww[j] >> 16;
+            out[2 * j] = prmt_sx(ww[j], 0x9910u);            // bytes 0,1 + sign of byte 1
+            out[2 * j + 1] = prmt_sx(ww[j], 0xbb32u);        // bytes 2,3 + sign of byte 3
         }
     } else {
         const uint4 w = ld_nc_u4(reinterpret_cast<const uint4 *>(base) + v);
         const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int j = 0; j < 16; ++j) out[j] = (int)(int8_t)((ww[j >> 2] >> ((j & 3) * 8)) & 0xff);
+        for (int j = 0; j < 4; ++j) {
+            out[4 * j] = prmt_sx(ww[j], 0x8880u);
+            out[4 * j + 1] = prmt_sx(ww[j], 0x9991u);
+            out[4 * j + 2] = prmt_sx(ww[j], 0xaaa2u);
+            out[4 * j + 3] = prmt_sx(ww[j], 0xbbb3u);
+        }
     }
 }
 
+__device__ __forceinline__ uint32_t pack4_sat_s8(int y0, int y1, int y2, int y3)
+{
+    uint32_t t, w;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(y3), "r"(y2), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(y1), "r"(y0), "r"(t));
+    return w;
+}
+
 // 16 elements per thread and iteration: 16 / 32-byte vector loads per operand, two 16-byte stores for the
-// int16 sum and one for the int8 requantisation (buffers are 16-byte aligned; scalar tail below)
-template <bool A16, bool B16>
+// int16 sum and one for the int8 requantisation (buffers are 16-byte aligned; scalar tail below).  The
+// kernel is instruction-bound before it is HBM-bound, so the per-element chain is kept to ~10
+// instructions: PRMT sign-extending unpack, the two input shifts as IMADs (fma pipe), a 2-op clamp, the
+// ties-to-even shift in 4 ops and saturation inside the packing instruction.
+//   RELU_IN: either operand carries a pending ReLU (rare once the ReLU is fused into the producer)
+//   QDOWN  : q_shift < 0 (the usual case: the Eltwise's feat bit is coarser than the exact sum)
+template <bool A16, bool B16, bool RELU_IN, bool QDOWN>
 __global__ void __launch_bounds__(kPipeThreads)
 add_requant_kernel(const AddParams p, size_t n)
 {
     const size_t nvec = n >> 4;
     const size_t stride = (size_t)gridDim.x * kPipeThreads;
+    const int a_mul = 1 << p.a_shift, b_mul = 1 << p.b_shift;
+    const int a_lo = p.a_relu ? 0 : -32768, b_lo = p.b_relu ? 0 : -32768;
+    const int d = QDOWN ? -p.q_shift : 0;
+    const int rc = QDOWN ? (1 << (d - 1)) - 1 : 0;
     for (size_t v = (size_t)blockIdx.x * kPipeThreads + threadIdx.x; v < nvec; v += stride) {
-        int av[16], bv[16];
+        int av[16], bv[16], num[16], q[16];
         add_load16<A16>(p.a, v, av);
         add_load16<B16>(p.b, v, bv);
-        uint32_t o16[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o8[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             int x = av[j], y = bv[j];
-            if (p.a_relu) x = max(x, 0);
-            if (p.b_relu) y = max(y, 0);
-            const int num = max(p.lo, min(p.hi, (x << p.a_shift) + (y << p.b_shift)));   // p.lo = 0 with a fused ReLU
-            o16[j >> 1] |= ((uint32_t)num & 0xffffu) << ((j & 1) * 16);
-            o8[j >> 2] |= ((uint32_t)requant_rne(num, p.q_shift) & 0xffu) << ((j & 3) * 8);
+            if (RELU_IN) { x = max(x, a_lo); y = max(y, b_lo); }
+            num[j] = max(p.lo, min(p.hi, x * a_mul + y * b_mul));       // p.lo = 0 with a fused output ReLU
+            if (QDOWN) q[j] = (num[j] + rc + ((num[j] >> d) & 1)) >> d;   // ties to even; the pack saturates
+            else q[j] = max(-128, min(127, num[j])) << p.q_shift;        // saturate first: |num| <= 2^15
         }
         if (p.out16) {
+            uint32_t o16[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o16[j] = __byte_perm((uint32_t)num[2 * j], (uint32_t)num[2 * j + 1], 0x5410);
             reinterpret_cast<uint4 *>(p.out16)[2 * v] = make_uint4(o16[0], o16[1], o16[2], o16[3]);
             reinterpret_cast<uint4 *>(p.out16)[2 * v + 1] = make_uint4(o16[4], o16[5], o16[6], o16[7]);
         }
-        if (p.out8) reinterpret_cast<uint4 *>(p.out8)[v] = make_uint4(o8[0], o8[1], o8[2], o8[3]);
+        if (p.out8)
+            reinterpret_cast<uint4 *>(p.out8)[v] =
+                make_uint4(pack4_sat_s8(q[0], q[1], q[2], q[3]), pack4_sat_s8(q[4], q[5], q[6], q[7]),
+                           pack4_sat_s8(q[8], q[9], q[10], q[11]), pack4_sat_s8(q[12], q[13], q[14], q[15]));
     }
     const size_t t = (nvec << 4) + (size_t)blockIdx.x * kPipeThreads + threadIdx.x;
     if (t < n) {
@@ -213,9 +248,19 @@ extern "C" int pq_add_requant_ex(const void *a, int a_is16, int a_bit, int a_rel
     p.q_shift = q_bit - o_bit; p.out16 = out16; p.out8 = out8;
     const unsigned int grid = pipe_grid((n >> 4) + 16);
     cudaStream_t s = (cudaStream_t)stream;
-    if (a_is16 && b_is16) pq::add_requant_kernel<true, true><<<grid, pq::kPipeThreads, 0, s>>>(p, n);
-    else if (a_is16) pq::add_requant_kernel<true, false><<<grid, pq::kPipeThreads, 0, s>>>(p, n);
-    else if (b_is16) pq::add_requant_kernel<false, true><<<grid, pq::kPipeThreads, 0, s>>>(p, n);
-    else pq::add_requant_kernel<false, false><<<grid, pq::kPipeThreads, 0, s>>>(p, n);
+    const int variant = (a_is16 ? 8 : 0) | (b_is16 ? 4 : 0) | ((a_relu || b_relu) ? 2 : 0) | (p.q_shift < 0 ? 1 : 0);
+#define PQ_ADD_CASE(V, A, B, R, Q) \
+    case V: pq::add_requant_kernel<A, B, R, Q><<<grid, pq::kPipeThreads, 0, s>>>(p, n); break;
+    switch (variant) {
+        PQ_ADD_CASE(0, false, false, false, false) PQ_ADD_CASE(1, false, false, false, true)
+        PQ_ADD_CASE(2, false, false, true, false) PQ_ADD_CASE(3, false, false, true, true)
+        PQ_ADD_CASE(4, false, true, false, false) PQ_ADD_CASE(5, false, true, false, true)
+        PQ_ADD_CASE(6, false, true, true, false) PQ_ADD_CASE(7, false, true, true, true)
+        PQ_ADD_CASE(8, true, false, false, false) PQ_ADD_CASE(9, true, false, false, true)
+        PQ_ADD_CASE(10, true, false, true, false) PQ_ADD_CASE(11, true, false, true, true)
+        PQ_ADD_CASE(12, true, true, false, false) PQ_ADD_CASE(13, true, true, false, true)
+        PQ_ADD_CASE(14, true, true, true, false) PQ_ADD_CASE(15, true, true, true, true)
+    }
+#undef PQ_ADD_CASE
     return (int)cudaGetLastError();
 }

@@ -96,10 +96,11 @@ def test_conv_s8_resnet50_geometries_vs_oracle(oracle, shape):
 # small-channel ("stem") convolutions: (B, Cin, H, W, Cout, k, stride, pad) incl. ragged patches (P, Q not
 # multiples of the 8 x 16 output patch), one channel, eight channels, 3x3 and 5x5 filters
 SMALLC_SHAPES = [(2, 3, 64, 64, 64, 7, 2, 3), (3, 3, 37, 53, 32, 7, 2, 3), (1, 1, 30, 30, 16, 3, 2, 1),
-                 (2, 8, 21, 19, 48, 5, 2, 2), (2, 4, 18, 10, 256, 3, 2, 0), (1, 3, 224, 224, 64, 7, 2, 3)]
+                 (2, 8, 21, 19, 48, 5, 2, 2), (2, 4, 18, 10, 256, 3, 2, 0), (1, 3, 224, 224, 64, 7, 2, 3),
+                 (2, 3, 33, 41, 32, 7, 4, 3), (1, 3, 40, 300, 72, 3, 2, 1)]
 
 
-@pytest.mark.parametrize("shape", SMALLC_SHAPES, ids=["b%d_c%d_%dx%d_o%d_k%d" % s[:6] for s in SMALLC_SHAPES])
+@pytest.mark.parametrize("shape", SMALLC_SHAPES, ids=["b%d_c%d_%dx%d_o%d_k%d_s%d" % s[:7] for s in SMALLC_SHAPES])
 @pytest.mark.parametrize("relu", [False, True])
 def test_smallc_conv_vs_oracle_and_im2col(oracle, shape, relu):
     """pq_quantize_nchw_to_padded_nhwc8_s8 + pq_conv2d_smallc_s8 (overlapping-window TMA) against the oracle's
