@@ -248,12 +248,24 @@ __device__ __forceinline__ int requant(int acc, const Requant &q, int bias)
     return min(127, requant_nohi(acc, q, bias));
 }
 
+// Accumulator stages in TMEM (<= 512 columns) == groups of epilogue warps working on different tiles.
+template <int BN> struct EpiCfg {
+    static constexpr int kAcc = BN == 256 ? 2 : 4;             // TMEM accumulator stages
+    static constexpr int kColSplit = BN == 256 ? 2 : 1;        // warps sharing the columns of one tile row block
+    static constexpr int kWarpsPerAcc = 4 * kColSplit;         // arrivals that release an accumulator
+    static constexpr int kCols = BN / kColSplit;               // columns per warp and tile: 128, 128, 64, 32
+    static constexpr int kSlab = kCols < 64 ? kCols : 64;      // bytes per staged row: one TMA store per slab
+    static constexpr int kSlabBytes = 32 * kSlab;              // warp-private staging buffer
+    static constexpr uint32_t kTmemCols = kAcc * BN < 32 ? 32 : kAcc * BN;
+    static_assert(kAcc * kWarpsPerAcc == kEpiWarps, "every epilogue warp has a (stage, quadrant, column part)");
+};
+
 template <int BN, int BK, int STAGES>
 struct GemmSmem {
     static constexpr int kABytes = kBM * BK;
     static constexpr int kBBytes = BN * BK;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kOutBytes = kBM * BN;       // int8 output staging tile (swizzled rows of <= 128 B)
+    static constexpr int kOutBytes = kEpiWarps * EpiCfg<BN>::kSlabBytes;   // warp-private int8 staging slabs
     static constexpr size_t kTotal = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + kOutBytes + 256 /*barriers*/;
 };
 
@@ -280,20 +292,24 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
                                          uint64_t *tmem_full_bar, uint64_t *tmem_empty_bar, uint32_t tmem_base,
                                          int total_tiles, int n_tiles)
 {
+    using E = EpiCfg<BN>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
-    const int part = (warp - 2) >> 2;              // which quarter of the tile's columns
-    constexpr int kCols = BN / 4;                  // columns per epilogue warp: 8, 16, 32 or 64
-    constexpr int kChunk = kCols < 16 ? kCols : 16;
-    constexpr int kChunks = kCols / kChunk;
-    constexpr int kRowBytes = BN < 128 ? BN : 128; // staging rows: sub-tiles of [128 rows][<= 128 bytes]
-    constexpr uint32_t kSwzMask = kRowBytes == 128 ? 7u : (kRowBytes == 64 ? 3u : 1u);
+    const int idx = (warp - 2) >> 2;               // 0..3
+    const int group = idx / E::kColSplit;          // which tiles (and which accumulator stage) this warp serves
+    const int part = idx % E::kColSplit;           // which column part of those tiles
+    constexpr int kCols = E::kCols, kSlab = E::kSlab;
+    constexpr int kChunksPerSlab = kSlab / 16, kSlabs = kCols / kSlab;
+    constexpr uint32_t kSwzMask = kSlab == 64 ? 3u : 1u;
+    uint8_t *stage_buf = smem_o + (warp - 2) * E::kSlabBytes;
     const int row = quad * 32 + lane;
     const Requant rq = make_requant(p.rs, p.relu);
     const float dq = __int_as_float((127 - p.ob) << 23);        // 2^-ob, exact
-    const bool store_thread = threadIdx.x == 64;                // issues / retires the TMA stores
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const bool staged = FAST || p.stage_s8;
+    uint32_t acc_phase = 0;
+    int it = 0;                                                  // position in this CTA's tile sequence
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        if ((it & (E::kAcc - 1)) != group) continue;
         const int m0 = (tile / n_tiles) * kBM, nt0 = (tile % n_tiles) * BN, n0 = nt0 + part * kCols;
         int m = m0 + row, p_img = 0, p_row = 0, p_col = 0;
         bool row_ok = m < p.M;
@@ -322,40 +338,28 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
             }
             if (p.out_s8 && !p.stage_s8) o8 = p.out_s8 + (size_t)m * p.N + n0;
         }
-        mbar_wait(tmem_full_bar + acc, acc_phase);
+        mbar_wait(tmem_full_bar + group, acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kCols);
-        uint32_t packed[kCols / 4];                // this thread's int8 results, 4 per word
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(group * BN + part * kCols);
 
-        // process one chunk of kChunk columns held in registers
-        auto emit = [&](const uint32_t (&a)[16], int c0) {
-            int y[16];
+        // one chunk of 16 columns held in registers -> packed int8 (4 words) [+ fp32 / unstaged int8 stores]
+        auto emit = [&](const uint32_t (&a)[16], int c0, uint32_t (&packed)[4]) {
             if (FAST) {
-                // N % 16 == 0 here, so a 16-column chunk is entirely inside or outside N (outside: the TMA
-                // store clips it, nothing to compute); bias is 64-byte aligned: 4 x LDG.128, warp-uniform
-                if (kChunk == 16) {
-                    if (n0 + c0 >= p.N) return;
-                    const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
+                // N % 16 == 0 here, so a chunk is entirely inside or outside N (outside: the TMA store clips
+                // it); bias is 64-byte aligned: 4 x LDG.128, warp-uniform
+                if (n0 + c0 >= p.N) return;
+                const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int4 b4 = __ldg(bp + j);
-                        packed[c0 / 4 + j] = pack4_sat_s8(requant_t<POS>((int)a[4 * j], rq, b4.x), requant_t<POS>((int)a[4 * j + 1], rq, b4.y),
-                                                          requant_t<POS>((int)a[4 * j + 2], rq, b4.z), requant_t<POS>((int)a[4 * j + 3], rq, b4.w));
-                    }
-                } else {                           // BN = 32: 8 columns per warp; N % 16 == 0 keeps them whole too
-                    if (n0 + c0 >= p.N) return;
-                    const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
-#pragma unroll
-                    for (int j = 0; j < kChunk / 4; ++j) {
-                        const int4 b4 = __ldg(bp + j);
-                        packed[c0 / 4 + j] = pack4_sat_s8(requant_t<POS>((int)a[4 * j], rq, b4.x), requant_t<POS>((int)a[4 * j + 1], rq, b4.y),
-                                                          requant_t<POS>((int)a[4 * j + 2], rq, b4.z), requant_t<POS>((int)a[4 * j + 3], rq, b4.w));
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const int4 b4 = __ldg(bp + j);
+                    packed[j] = pack4_sat_s8(requant_t<POS>((int)a[4 * j], rq, b4.x), requant_t<POS>((int)a[4 * j + 1], rq, b4.y),
+                                             requant_t<POS>((int)a[4 * j + 2], rq, b4.z), requant_t<POS>((int)a[4 * j + 3], rq, b4.w));
                 }
                 return;
             }
-            const bool full = n0 + c0 + kChunk <= p.N;
-            if (full && kChunk == 16) {
+            int y[16];
+            const bool full = n0 + c0 + 16 <= p.N;
+            if (full) {
                 const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -365,94 +369,87 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < kChunk; ++j)
+                for (int j = 0; j < 16; ++j)
                     y[j] = requant_t<POS>((int)a[j], rq, n0 + c0 + j < p.N ? __ldg(p.bias + n0 + c0 + j) : 0);
             }
 #pragma unroll
-            for (int j = 0; j < kChunk / 4; ++j)       // the pack saturates from above
-                packed[c0 / 4 + j] = pack4_sat_s8(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)                // the pack saturates from above
+                packed[j] = pack4_sat_s8(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
             if (!(row_ok && n0 + c0 < p.N)) return;
             if (of) {
                 if (p.hw > 1) {
 #pragma unroll
-                    for (int j = 0; j < kChunk; ++j)
+                    for (int j = 0; j < 16; ++j)
                         if (full || n0 + c0 + j < p.N) of[(size_t)(c0 + j) * cstride] = __fmul_rn((float)min(127, y[j]), dq);
                 } else if (full && (p.N & 3) == 0) {
 #pragma unroll
-                    for (int j = 0; j < kChunk / 4; ++j)
+                    for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<float4 *>(of + c0 + 4 * j) =
                             make_float4(__fmul_rn((float)min(127, y[4 * j]), dq), __fmul_rn((float)min(127, y[4 * j + 1]), dq),
                                         __fmul_rn((float)min(127, y[4 * j + 2]), dq), __fmul_rn((float)min(127, y[4 * j + 3]), dq));
                 } else {
 #pragma unroll
-                    for (int j = 0; j < kChunk; ++j)
+                    for (int j = 0; j < 16; ++j)
                         if (full || n0 + c0 + j < p.N) of[c0 + j] = __fmul_rn((float)min(127, y[j]), dq);
                 }
             }
             if (o8) {                                  // unstaged fall-back (N % 16 != 0): direct stores
 #pragma unroll
-                for (int j = 0; j < kChunk; ++j)
+                for (int j = 0; j < 16; ++j)
                     if (full || n0 + c0 + j < p.N) o8[c0 + j] = (int8_t)min(127, y[j]);
             }
         };
-        auto load = [&](uint32_t (&a)[16], int c0) {
-            if (kChunk == 16) tmem_ld16(taddr + (uint32_t)c0, a); else tmem_ld8(taddr + (uint32_t)c0, a);
-        };
 
-        // software pipeline: the TMEM load of chunk i+1 is in flight while chunk i is processed
+        // software pipeline over the chunks of the tile: the TMEM load of chunk i+1 is in flight while chunk
+        // i is processed; after each slab (kSlab columns) the warp stages and TMA-stores its 32 rows.
         uint32_t a0[16], a1[16];
-        load(a0, 0);
+        uint32_t packed[kChunksPerSlab][4];
+        constexpr int kChunks = kCols / 16;
+        tmem_ld16(taddr, a0);
 #pragma unroll
-        for (int ch = 0; ch < kChunks; ch += 2) {
+        for (int ch = 0; ch < kChunks; ++ch) {
             tmem_ld_wait();
-            if (ch + 1 < kChunks) load(a1, (ch + 1) * kChunk);
-            emit(a0, ch * kChunk);
             if (ch + 1 < kChunks) {
-                tmem_ld_wait();
-                if (ch + 2 < kChunks) load(a0, (ch + 2) * kChunk);
-                emit(a1, (ch + 1) * kChunk);
+                if (ch & 1) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), a0);
+                else tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), a1);
+            } else {
+                // every TMEM read of this accumulator has completed: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar + group);
             }
-        }
-        // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-
-        if (FAST || p.stage_s8) {
-            // The previous tile's TMA store must have finished reading the staging tile.
-            if (store_thread) bulk_wait_read0();
-            epi_bar_sync(32 * kEpiWarps);
-            const int col0 = part * kCols;                          // byte column inside the tile
-            uint8_t *sub = smem_o + (col0 / kRowBytes) * (kBM * kRowBytes);
-            const uint32_t off = (uint32_t)(row * kRowBytes + (col0 % kRowBytes));
-            if (kCols >= 16) {
+            if (ch & 1) emit(a1, ch * 16, packed[ch % kChunksPerSlab]);
+            else emit(a0, ch * 16, packed[ch % kChunksPerSlab]);
+            if (staged && (ch % kChunksPerSlab) == kChunksPerSlab - 1) {
+                const int slab = ch / kChunksPerSlab;
+                const int colb = n0 + slab * kSlab;                     // first output channel of the slab
+                if (colb < p.N) {                                       // warp-uniform
+                    // the previous TMA store of this warp must have finished reading the staging buffer
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
 #pragma unroll
-                for (int j = 0; j < kCols / 16; ++j) {
-                    const uint32_t o = off + 16u * j;
-                    *reinterpret_cast<uint4 *>(sub + (o ^ (((o >> 7) & kSwzMask) << 4))) =
-                        make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                }
-            } else {                                                // BN = 32: 8 bytes per thread
-                *reinterpret_cast<uint2 *>(sub + (off ^ (((off >> 7) & kSwzMask) << 4))) =
-                    make_uint2(packed[0], packed[kCols / 4 - 1]);
-            }
-            fence_proxy_async();
-            epi_bar_sync(32 * kEpiWarps);
-            if (store_thread) {
-#pragma unroll
-                for (int sb = 0; sb < BN / kRowBytes; ++sb)
-                    if (nt0 + sb * kRowBytes < p.N) {
-                        if (p.a_im2col == 2)
-                            tma_store_4d(tmap_o, smem_o + sb * (kBM * kRowBytes), nt0 + sb * kRowBytes, p_col, p_row, p_img);
-                        else
-                            tma_store_2d(tmap_o, smem_o + sb * (kBM * kRowBytes), nt0 + sb * kRowBytes, m0);
+                    for (int j = 0; j < kChunksPerSlab; ++j) {
+                        const uint32_t o = (uint32_t)(lane * kSlab + 16 * j);
+                        *reinterpret_cast<uint4 *>(stage_buf + (o ^ (((o >> 7) & kSwzMask) << 4))) =
+                            make_uint4(packed[j][0], packed[j][1], packed[j][2], packed[j][3]);
                     }
-                bulk_commit();
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.a_im2col == 2) {     // 32 tile rows = a (32 / TW) x min(TW, 32) piece of the patch
+                            const int r0 = quad * 32;
+                            tma_store_4d(tmap_o, stage_buf, colb, p_col + (r0 & (p.TW - 1)), p_row + (r0 >> p.tw_shift), p_img);
+                        } else {
+                            tma_store_2d(tmap_o, stage_buf, colb, m0 + quad * 32);
+                        }
+                        bulk_commit();
+                    }
+                }
             }
         }
+        acc_phase ^= 1;
     }
-    if ((FAST || p.stage_s8) && store_thread) bulk_wait_read0();
+    if (staged && lane == 0) bulk_wait_read0();
 }
 
 template <int BN, int BK, int STAGES>
@@ -468,12 +465,13 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t *smem_o = smem + (size_t)STAGES * Cfg::kStageBytes;          // 1024-byte aligned
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_o + Cfg::kOutBytes);
     uint64_t *empty_bar = full_bar + STAGES;
-    uint64_t *tmem_full_bar = empty_bar + STAGES;      // [2]
-    uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+    uint64_t *tmem_full_bar = empty_bar + STAGES;      // [kAcc]
+    uint64_t *tmem_empty_bar = tmem_full_bar + 4;      // [kAcc]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 4);
+    constexpr int kAcc = EpiCfg<BN>::kAcc;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+    constexpr uint32_t kTmemCols = EpiCfg<BN>::kTmemCols;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int total_tiles = (p.a_im2col == 2 ? p.M / kBM : (p.M + kBM - 1) / kBM) * n_tiles;   // mode 2: M = patches * 128
 
@@ -482,7 +480,7 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         if (p.stage_s8) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, kEpiWarps); }
+        for (int s = 0; s < kAcc; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, EpiCfg<BN>::kWarpsPerAcc); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -556,7 +554,7 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tmem_full_bar + acc);      // accumulator complete
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -611,17 +609,18 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int n_tiles = (p.N + BN - 1) / BN;
     uint8_t *smem_b = smem;                                              // [n_tiles][R][64 filters][64 B], 64B swizzle
-    uint8_t *smem_o = smem_b + (size_t)n_tiles * p.R * (BN * BK);       // 8 KB, 1024-byte aligned
-    uint8_t *smem_a = smem_o + kBM * BN;                                 // ring of raw input rows
+    uint8_t *smem_o = smem_b + (size_t)n_tiles * p.R * (BN * BK);       // warp-private output slabs, 1024-byte aligned
+    uint8_t *smem_a = smem_o + kEpiWarps * EpiCfg<BN>::kSlabBytes;       // ring of raw input rows
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_a + (size_t)rp.stages * rp.a_stage);
     uint64_t *empty_bar = full_bar + kMaxStages;
     uint64_t *tmem_full_bar = empty_bar + kMaxStages;
-    uint64_t *tmem_empty_bar = tmem_full_bar + 2;
-    uint64_t *b_bar = tmem_empty_bar + 2;
+    uint64_t *tmem_empty_bar = tmem_full_bar + 4;
+    uint64_t *b_bar = tmem_empty_bar + 4;
+    constexpr int kAcc = EpiCfg<BN>::kAcc;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t kTmemCols = 2 * BN;
+    constexpr uint32_t kTmemCols = EpiCfg<BN>::kTmemCols;
     const int total_tiles = (p.M / kBM) * n_tiles;
     const int per_img = p.tiles_p * p.tiles_q;
 
@@ -629,7 +628,7 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
         for (int s = 0; s < rp.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, kEpiWarps); }
+        for (int s = 0; s < kAcc; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, EpiCfg<BN>::kWarpsPerAcc); }
         mbar_init(b_bar, 1);
         fence_barrier_init();
     }
@@ -683,7 +682,7 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
                 umma_commit(empty_bar + stage);
                 umma_commit(tmem_full_bar + acc);
                 if (++stage == rp.stages) { stage = 0; phase ^= 1; }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -809,16 +808,17 @@ int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, 
     CUtensorMap to = {};
     p.stage_s8 = 0;
     if (p.out_s8 && (p.N & 15) == 0 && (((uintptr_t)p.out_s8) & 15) == 0) {
-        constexpr int kRowBytes = BN < 128 ? BN : 128;
+        constexpr int kSlab = pq::EpiCfg<BN>::kSlab;       // each epilogue warp stores [32 rows][kSlab bytes] boxes
         int rc;
         if (p.a_im2col == 2) {                     // NHWC output addressed by (channel, q, p, image): TH x TW patches
             const cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.Q, (cuuint64_t)p.P,
                                         (cuuint64_t)(p.M / pq::kBM / (p.tiles_p * p.tiles_q))};
             const cuuint64_t strides[3] = {(cuuint64_t)p.N, (cuuint64_t)p.N * p.Q, (cuuint64_t)p.N * p.Q * p.P};
-            const cuuint32_t box[4] = {(cuuint32_t)kRowBytes, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-            rc = encode_nd(&to, p.out_s8, 4, dims, strides, box, kRowBytes);
+            const cuuint32_t box[4] = {(cuuint32_t)kSlab, (cuuint32_t)(p.TW < 32 ? p.TW : 32),
+                                       (cuuint32_t)(p.TW < 32 ? 32 / p.TW : 1), 1};
+            rc = encode_nd(&to, p.out_s8, 4, dims, strides, box, kSlab);
         } else {
-            rc = encode_2d(&to, p.out_s8, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.N, kRowBytes, pq::kBM);
+            rc = encode_2d(&to, p.out_s8, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.N, kSlab, 32);
         }
         if (rc != PQ_OK) return rc;
         p.stage_s8 = 1;
@@ -976,7 +976,7 @@ extern "C" int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const
         const int pitch = Wp * kPix;
         const int tiles_q = (d.Q + pq::kBM - 1) / pq::kBM;
         const int a_stage = (d.R * pitch + 2112 + 1023) / 1024 * 1024;       // + over-read of the last window rows
-        const long long fixed = 1024 + (long long)n_tiles * d.R * 4096 + pq::kBM * 64 + 256;
+        const long long fixed = 1024 + (long long)n_tiles * d.R * 4096 + pq::kEpiWarps * pq::EpiCfg<64>::kSlabBytes + 256;
         const long long stages_fit = (227 * 1024 - fixed) / a_stage;
         const long long tiles_m = (long long)d.N * d.P * tiles_q;
         if (stages_fit >= 2 && tiles_m * pq::kBM <= 0x7fffffffLL &&
@@ -994,7 +994,7 @@ extern "C" int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const
             if (q.out_s8 && (q.N & 15) == 0 && (((uintptr_t)q.out_s8) & 15) == 0) {
                 const cuuint64_t odims[4] = {(cuuint64_t)q.N, (cuuint64_t)q.Q, (cuuint64_t)q.P, (cuuint64_t)d.N};
                 const cuuint64_t ostr[3] = {(cuuint64_t)q.N, (cuuint64_t)q.N * q.Q, (cuuint64_t)q.N * q.Q * q.P};
-                const cuuint32_t obox[4] = {64, (cuuint32_t)q.TW, 1, 1};
+                const cuuint32_t obox[4] = {64, 32, 1, 1};            // one epilogue warp: 32 output columns x 64 channels
                 if ((rc = encode_nd(&to, q.out_s8, 4, odims, ostr, obox, 64)) != PQ_OK) return rc;
                 q.stage_s8 = 1;
             }
