@@ -140,6 +140,25 @@ def ncu_traffic(kernel):
         return None
 
 
+def fakequant_bandwidth(n_elems=1 << 28, iters=10):
+    """Second half of BASELINE.json's metric: QuanDequan (pq_fakequant_f32) GB/s on a 1 GiB fp32 tensor
+    (larger than L2), 8 algorithmic bytes per element, CUDA events on the launching stream."""
+    from common.quantity import _native
+    x = torch.randn(n_elems, device="cuda")
+    for _ in range(3):
+        y = _native.fakequant(x, 4)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(iters):
+        y = _native.fakequant(x, 4)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    del x, y
+    return 8.0 * n_elems / (ms * 1e-3) / 1e9, ms
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_job(net, batches, n_global, workdir, rank, world):
     """One whole calibration job through the public API; returns (seconds on device, Quantity)."""
@@ -255,6 +274,7 @@ def ours(args):
     assert q2.last_calibration["bits"]["image"] == bits_image
     del host_batches
 
+    fq_gbps, fq_ms = fakequant_bandwidth()
     line = None
     if rank == 0:
         cpu = cpu_baseline(sample_images=args.cpu_sample) if world == 1 and not args.no_cpu_baseline else None
@@ -268,6 +288,8 @@ def ours(args):
                                     % (timings.get("cached_batches", 0), K),
                            "parallelism": "dp%d" % world},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                "fakequant": {"GBps": round(fq_gbps, 1), "frac_of_hbm_peak": round(fq_gbps / peak, 4),
+                              "elements": 1 << 28, "ms": round(fq_ms, 4), "algorithmic_bytes_per_element": 8},
                 "phases_s": {k: round(v, 4) for k, v in timings.items() if k.endswith("_s")}}
         if cpu:
             line["cpu_baseline"] = cpu

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--s8-out", action="store_true", help="store int8 NHWC instead of fp32 NCHW")
     ap.add_argument("--only", type=int, default=None, help="run only this row of the table (for ncu captures)")
+    ap.add_argument("--fused-add", action="store_true", help="conv + NewAdd + ReLU in one kernel (int16 shortcut)")
     args = ap.parse_args()
     B = args.batch
     tot_conv = tot_q = tot_ops = 0.0
@@ -70,6 +71,11 @@ def main():
             t_q = time_ms(lambda: _native.quantize_im2col_s8(x, 4, (k, k), (s, s), (pad, pad), kp))
             t_c = time_ms(lambda: _native.gemm_s8(q, wn, bias, 9, 4, hw=P * P, want_f32=not args.s8_out,
                                                   want_s8=args.s8_out))
+        elif args.fused_add:
+            q = _native.quantize_nchw_to_nhwc_s8(x, 4, cpad)
+            t_q = 0.0
+            sc = torch.randint(-2000, 2000, (B, P, P, cout), dtype=torch.int16, device="cuda")
+            t_c = time_ms(lambda: _native.conv2d_s8_add(q, wk, bias, (s, s), (pad, pad), 9, 4, sc, 5, False, 4, True))
         else:
             q = _native.quantize_nchw_to_nhwc_s8(x, 4, cpad)
             t_q = time_ms(lambda: _native.quantize_nchw_to_nhwc_s8(x, 4, cpad))

@@ -191,7 +191,7 @@ def emit_line(mode, model_name, batch, label, ms, stats, launches, peak_hbm):
     if mode == "model":
         peak = int8_peak_tops()
         line["int8_peak_TOPS_measured"] = round(peak, 1)
-        for name in ("conv_s8", "gemm_s8"):
+        for name in ("conv_s8", "gemm_s8", "conv_add_s8"):
             if name in stats and stats[name]["ms_per_fwd"] > 0:
                 tops = stats[name]["alg_bytes_per_fwd"] / (stats[name]["ms_per_fwd"] * 1e-3) / 1e12
                 line["kernels"][name]["int8_ops_per_fwd"] = line["kernels"][name].pop("alg_bytes_per_fwd")

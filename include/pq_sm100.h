@@ -186,6 +186,23 @@ int pq_add_requant_ex(const void *a, int a_is16, int a_bit, int a_relu, const vo
                       int b_relu, size_t n, int flags, int16_t *out16, int8_t *out8, int q_bit,
                       pq_stream_t stream);
 
+/* NewConv2d + NewAdd (+ the nn.ReLU after the Eltwise) in ONE kernel: the conv / GEMM epilogue adds the
+ * shortcut operand and writes the exact int16 sum and its int8 requantisation, exactly as pq_add_requant_ex
+ * would on the conv's int8 result (which is never written to memory).  conv operand: y at bit `ob` of the
+ * conv descriptor; shortcut: int8 or int16 [M][N] row-major (NHWC) at bit shortcut_bit.  N % 16 == 0. */
+typedef struct pq_add_desc {
+    const void *shortcut;
+    int shortcut_is16, shortcut_bit, shortcut_relu;
+    int out_relu;            /* nn.ReLU after the Eltwise */
+    int q_bit;               /* the Eltwise's feat bit: out8 = Quantity(q_bit)(sum) */
+    int16_t *out16;          /* exact sum at o_bit = max(ob, shortcut_bit); may be NULL */
+    int8_t *out8;            /* required */
+} pq_add_desc;
+int pq_gemm_s8_add(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs, int ob,
+                   const pq_add_desc *add_host, pq_stream_t stream);
+int pq_conv2d_s8_add(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
+                     const pq_conv_desc *desc_host, const pq_add_desc *add_host, pq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

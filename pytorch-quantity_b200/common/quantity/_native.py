@@ -40,6 +40,8 @@ SYMBOLS = {
     "pq_conv2d_s8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pq_gemm_s8_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pq_conv2d_s8_ex": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "pq_gemm_s8_add": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pq_conv2d_s8_add": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "pq_relu_s8": (_i, [_vp, _vp, _sz, _vp]),
     "pq_maxpool_nhwc_s8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pq_add_requant": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _sz, _vp, _vp, _i, _vp]),
@@ -53,6 +55,13 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
                 ("N", "H", "W", "C", "K", "R", "S", "stride_h", "stride_w", "pad_h", "pad_w",
                  "P", "Q", "rs", "ob")]
+
+
+class AddDesc(ctypes.Structure):
+    """struct pq_add_desc"""
+    _fields_ = [("shortcut", ctypes.c_void_p), ("shortcut_is16", ctypes.c_int), ("shortcut_bit", ctypes.c_int),
+                ("shortcut_relu", ctypes.c_int), ("out_relu", ctypes.c_int), ("q_bit", ctypes.c_int),
+                ("out16", ctypes.c_void_p), ("out8", ctypes.c_void_p)]
 
 
 _lib = None
@@ -322,6 +331,29 @@ def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, wa
                                     FLAG_RELU if relu else 0, out_f32.data_ptr() if want_f32 else None,
                                     out_s8.data_ptr() if want_s8 else None, _stream(x_nhwc)), "pq_conv2d_s8")
     return out_f32, out_s8
+
+
+def conv2d_s8_add(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, shortcut, shortcut_bit, shortcut_relu, q_bit,
+                  out_relu, want16=True, c_real=None):
+    """NewConv2d + NewAdd (+ ReLU) in one kernel: returns (int16 exact sum or None, int8 at q_bit), both NHWC.
+    `shortcut` is int8 or int16 with the conv output's [N][P][Q][K] shape."""
+    require_cuda(x_nhwc, "conv2d_s8_add")
+    N, H, W, C = x_nhwc.shape
+    K, R, S, C2 = w_krsc.shape
+    assert C == C2
+    P = (H + 2 * padding[0] - R) // stride[0] + 1
+    Q = (W + 2 * padding[1] - S) // stride[1] + 1
+    assert tuple(shortcut.shape) == (N, P, Q, K) and shortcut.is_contiguous()
+    d = ConvDesc(N, H, W, C, K, R, S, stride[0], stride[1], padding[0], padding[1], P, Q, int(rs), int(ob))
+    out16 = torch.empty((N, P, Q, K), dtype=torch.int16, device=x_nhwc.device) if want16 else None
+    out8 = torch.empty((N, P, Q, K), dtype=torch.int8, device=x_nhwc.device)
+    add = AddDesc(shortcut.data_ptr(), 1 if shortcut.dtype == torch.int16 else 0, int(shortcut_bit),
+                  1 if shortcut_relu else 0, 1 if out_relu else 0, int(q_bit),
+                  out16.data_ptr() if want16 else None, out8.data_ptr())
+    with _Timed("conv_add_s8", 1, 2 * N * P * Q * K * R * S * (c_real or C), x_nhwc.device):        # int8 ops
+        check(lib().pq_conv2d_s8_add(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
+                                     ctypes.byref(add), _stream(x_nhwc)), "pq_conv2d_s8_add")
+    return out16, out8
 
 
 def relu_s8(x):

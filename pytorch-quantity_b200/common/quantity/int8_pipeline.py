@@ -23,24 +23,62 @@ import torch.nn.functional as F
 from . import _native
 
 
+# NewConv2d + NewAdd (+ ReLU) in one kernel (pq_conv2d_s8_add).  Bit-identical, but on B200 the fused
+# epilogue is instruction-bound and currently slower than the HBM-bound pq_add_requant_ex it replaces
+# (ResNet-50 batch 512: 5.5 ms vs 1.3 + 2.8 ms), so it is off by default; see DESIGN.md section 4.
+FUSE_ADD_INTO_CONV = False
+
 _METADATA = {"__get__", "size", "dim", "numel", "element_size", "ndimension", "is_floating_point", "__len__",
              "get_device", "is_complex", "nelement"}
+
+
+class _LazyConv:
+    """A NewConv2d whose kernel has not run yet.  If its only consumer turns out to be a NewAdd, the add
+    (and the ReLU after it) run inside the conv's epilogue and the conv result never touches memory."""
+
+    def __init__(self, mod, q):
+        self.mod, self.q, self.out = mod, q, None
+
+    def get(self):
+        if self.out is None:
+            mod, conv = self.mod, self.mod.Conv
+            _, self.out = _native.conv2d_s8(self.q, mod._w_krsc, mod._bias_i32, conv.stride, conv.padding, mod.rs_bit,
+                                            mod.output_bit, want_f32=False, want_s8=True, c_real=conv.in_channels,
+                                            relu=mod._fuse_relu)
+            self.q = None
+        return self.out
 
 
 class _LazyAdd:
     """A NewAdd whose kernel has not run yet: it runs when the first consumer asks for a payload, by
     which time it is known whether an nn.ReLU sits between the Eltwise and that consumer."""
 
-    def __init__(self, a, abit, arelu, b, bbit, brelu, q_bit):
-        self.args = (a, abit, arelu, b, bbit, brelu, q_bit)
-        self.o_bit = max(abit, bbit)
+    def __init__(self, x, y, q_bit):
+        self.x, self.y = x, y                          # operand QTensors (not yet materialised)
         self.q_bit = q_bit
         self.done = {}                                 # relu -> (s16, q8)
 
+    @staticmethod
+    def _fusable(t):
+        lc = t._lazy_conv
+        return FUSE_ADD_INTO_CONV and lc is not None and lc.out is None and not t.relu_pending and not lc.mod._fuse_relu \
+            and lc.mod.Conv.out_channels % 16 == 0
+
     def get(self, relu):
         if relu not in self.done:
-            a, abit, arelu, b, bbit, brelu, q_bit = self.args
-            self.done[relu] = _native.add_requant(a, abit, arelu, b, bbit, brelu, q_bit, out_relu=relu)
+            x, y = self.x, self.y
+            if not self._fusable(x) and self._fusable(y):
+                x, y = y, x
+            if self._fusable(x):                       # conv + add (+ relu) in one kernel
+                lc = x._lazy_conv
+                mod, conv = lc.mod, lc.mod.Conv
+                sc, sc_bit, sc_relu = _operand(y)
+                self.done[relu] = _native.conv2d_s8_add(lc.q, mod._w_krsc, mod._bias_i32, conv.stride, conv.padding,
+                                                        mod.rs_bit, mod.output_bit, sc, sc_bit, sc_relu, self.q_bit,
+                                                        relu, c_real=conv.in_channels)
+            else:
+                (a, abit, arelu), (b, bbit, brelu) = _operand(x), _operand(y)
+                self.done[relu] = _native.add_requant(a, abit, arelu, b, bbit, brelu, self.q_bit, out_relu=relu)
         return self.done[relu]
 
 
@@ -53,15 +91,23 @@ class QTensor(torch.Tensor):
                                                    requires_grad=False)
 
     def __init__(self, shape, device, q8=None, q8_bit=None, s16=None, s16_bit=None, relu_pending=False,
-                 nonneg=False, lazy=None):
+                 nonneg=False, lazy=None, lazy_conv=None):
         self._q8, self.q8_bit = q8, q8_bit             # int8 NHWC, value = q8 / 2^q8_bit (after pending relu)
         self._s16, self.s16_bit = s16, s16_bit         # int16 NHWC exact value (outputs of NewAdd)
         self.relu_pending = relu_pending               # a ReLU was applied logically but not to the payloads
         self.nonneg = nonneg                           # payloads are already >= 0
         self._lazy = lazy                              # _LazyAdd: payloads appear on first use
+        self._lazy_conv = lazy_conv                    # _LazyConv: the int8 payload appears on first use
         self._q8_relu = None
 
+    def exact_bit(self):
+        """Fractional bit of the most exact payload, without materialising anything."""
+        return self.s16_bit if self.s16_bit is not None else self.q8_bit
+
     def _materialize(self):
+        if self._lazy_conv is not None:
+            self._q8 = self._lazy_conv.get()
+            self._lazy_conv = None
         if self._lazy is not None:
             relu = self.relu_pending
             self._s16, self._q8 = self._lazy.get(relu)  # the pending ReLU is applied by the add kernel
@@ -107,7 +153,7 @@ class QTensor(torch.Tensor):
         if self.nonneg:
             return self
         return QTensor(self.shape, self.device, q8=self._q8, q8_bit=self.q8_bit, s16=self._s16,
-                       s16_bit=self.s16_bit, relu_pending=True, lazy=self._lazy)
+                       s16_bit=self.s16_bit, relu_pending=True, lazy=self._lazy, lazy_conv=self._lazy_conv)
 
     # ---- dispatch -------------------------------------------------------------------------
     @classmethod
@@ -187,11 +233,12 @@ def conv_forward(mod, x):
                        q8_bit=mod.output_bit, nonneg=mod._fuse_relu)
     else:
         q = _native.quantize_nchw_to_nhwc_s8(x, mod.input_bit, mod._c_pad)
-    _, out8 = _native.conv2d_s8(q, mod._w_krsc, mod._bias_i32, conv.stride, conv.padding, mod.rs_bit,
-                                mod.output_bit, want_f32=False, want_s8=True, c_real=conv.in_channels,
-                                relu=mod._fuse_relu)
-    N, P, Q, K = out8.shape
-    return QTensor((N, K, P, Q), out8.device, q8=out8, q8_bit=mod.output_bit, nonneg=mod._fuse_relu)
+    N, H, W, _ = q.shape
+    (R, S), (sh, sw), (ph, pw) = conv.kernel_size, conv.stride, conv.padding
+    P, Q = (H + 2 * ph - R) // sh + 1, (W + 2 * pw - S) // sw + 1
+    # deferred: a NewAdd consumer can absorb this convolution into one fused kernel
+    return QTensor((N, conv.out_channels, P, Q), q.device, q8_bit=mod.output_bit, nonneg=mod._fuse_relu,
+                   lazy_conv=_LazyConv(mod, q))
 
 
 def _operand(t):
@@ -208,13 +255,13 @@ def add_forward(mod, x, y):
     if not (isinstance(x, QTensor) and isinstance(y, QTensor)) or x.shape != y.shape:
         return None
     q_bit = getattr(mod, "output_bit", None)
-    (a, abit, arelu), (b, bbit, brelu) = _operand(x), _operand(y)
-    o_bit = max(abit, bbit)
-    if q_bit is None or a.shape != b.shape or not (0 <= o_bit <= 7) or o_bit - min(abit, bbit) > 7 \
-            or abs(q_bit - o_bit) > 15:
+    abit, bbit = x.exact_bit(), y.exact_bit()
+    if q_bit is None or abit is None or bbit is None:
         return None
-    return QTensor(x.shape, x.device, q8_bit=q_bit, s16_bit=o_bit,
-                   lazy=_LazyAdd(a, abit, arelu, b, bbit, brelu, q_bit))
+    o_bit = max(abit, bbit)
+    if not (0 <= o_bit <= 7) or o_bit - min(abit, bbit) > 7 or abs(q_bit - o_bit) > 15:
+        return None
+    return QTensor(x.shape, x.device, q8_bit=q_bit, s16_bit=o_bit, lazy=_LazyAdd(x, y, q_bit))
 
 
 def enable_int8_pipeline(model, enabled=True):

@@ -124,6 +124,21 @@ __device__ __forceinline__ uint32_t pack4_sat_s8(int y0, int y1, int y2, int y3)
     asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(y1), "r"(y0), "r"(t));
     return w;
 }
+// byte permute with sign replication (selector nibble bit 3): sign-extends one packed int8 / int16 lane
+__device__ __forceinline__ int prmt_sx(uint32_t w, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0u), "r"(sel));
+    return (int)d;
+}
+__device__ __forceinline__ uint4 ldg_nc_u4(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -209,6 +224,12 @@ struct GemmParams {
     // NHWC image with 8-byte pixels, so the S taps of one filter row are BK contiguous bytes and an
     // overlapping-stride tensor map (pixel step = stride_w * 8 bytes) fetches them for a TH x TW patch of
     // output pixels in one tiled TMA; K loop = the R filter rows.
+    // Fused NewAdd (int8 pipeline): the epilogue adds a shortcut tensor of the output's [M][N] geometry,
+    //   num = clamp(y * 2^add_cshift + shortcut * 2^add_sshift, add_lo, add_hi)        (units of 2^-o_bit)
+    // and writes num as int16 (out16) and round_half_even(num * 2^add_qshift) saturated as int8 (out_s8).
+    const void *add_sc;        // shortcut, int8 or int16 (add_is16); NULL: no fused add
+    int add_is16, add_sc_relu, add_cshift, add_sshift, add_lo, add_hi, add_qshift;
+    int16_t *out16;
     int tw_shift, TW, TH;      // output patch of one tile: TH x TW = 128 pixels, TW = 1 << tw_shift
     int tiles_p, tiles_q;      // patches per image
     const int32_t *bias;       // [N] quantised bias (already saturated to int8 range)
@@ -249,15 +270,20 @@ __device__ __forceinline__ int requant(int acc, const Requant &q, int bias)
 }
 
 // Accumulator stages in TMEM (<= 512 columns) == groups of epilogue warps working on different tiles.
-template <int BN> struct EpiCfg {
-    static constexpr int kAcc = BN == 256 ? 2 : 4;             // TMEM accumulator stages
-    static constexpr int kColSplit = BN == 256 ? 2 : 1;        // warps sharing the columns of one tile row block
-    static constexpr int kWarpsPerAcc = 4 * kColSplit;         // arrivals that release an accumulator
-    static constexpr int kCols = BN / kColSplit;               // columns per warp and tile: 128, 128, 64, 32
-    static constexpr int kSlab = kCols < 64 ? kCols : 64;      // bytes per staged row: one TMA store per slab
-    static constexpr int kSlabBytes = 32 * kSlab;              // warp-private staging buffer
+// FAST (int8-only, staged) epilogues are instruction-bound: 2-4 tiles in flight, one warp per (tile, lane
+// quadrant[, column half]).  The generic epilogue (fp32 NCHW stores, unstaged int8) is store-bound and
+// does best when all 16 warps drain ONE tile at a time (its 128 x BN x 4 bytes leave as one burst).
+template <int BN, bool FAST = true> struct EpiCfg {
+    static constexpr int kAcc = (FAST && BN < 256) ? 4 : 2;            // TMEM accumulator stages
+    static constexpr int kGroups = FAST ? kAcc : (BN >= 64 ? 1 : 2);   // warp groups on different tiles
+    static constexpr int kWarpsPerAcc = kEpiWarps / kGroups;           // arrivals that release an accumulator
+    static constexpr int kColSplit = kWarpsPerAcc / 4;                 // warps sharing the columns of one 32-row block
+    static constexpr int kCols = BN / kColSplit;                       // columns per warp and tile
+    static constexpr int kSlab = FAST ? (kCols < 64 ? kCols : 64) : kCols;   // bytes per staged row (FAST only)
+    static constexpr int kSlabBytes = 32 * kSlab;                      // warp-private staging buffer
     static constexpr uint32_t kTmemCols = kAcc * BN < 32 ? 32 : kAcc * BN;
-    static_assert(kAcc * kWarpsPerAcc == kEpiWarps, "every epilogue warp has a (stage, quadrant, column part)");
+    static_assert(kCols % 16 == 0 && kCols >= 16, "16-column chunks");
+    static_assert(!FAST || kSlab >= 32, "staged rows of >= 32 bytes");
 };
 
 template <int BN, int BK, int STAGES>
@@ -265,7 +291,7 @@ struct GemmSmem {
     static constexpr int kABytes = kBM * BK;
     static constexpr int kBBytes = BN * BK;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kOutBytes = kEpiWarps * EpiCfg<BN>::kSlabBytes;   // warp-private int8 staging slabs
+    static constexpr int kOutBytes = kEpiWarps * EpiCfg<BN, true>::kSlabBytes;   // warp-private int8 staging slabs (FAST is the larger)
     static constexpr size_t kTotal = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + kOutBytes + 256 /*barriers*/;
 };
 
@@ -287,12 +313,12 @@ __device__ __forceinline__ int requant_t(int acc, const Requant &q, int bias)
     return __viaddmax_s32(r, bias, q.lo);                     // max(r + bias, lo); callers saturate from above
 }
 
-template <int BN, bool POS, bool FAST>
+template <int BN, bool POS, bool FAST, bool ADD = false>
 __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap *tmap_o, uint8_t *smem_o,
                                          uint64_t *tmem_full_bar, uint64_t *tmem_empty_bar, uint32_t tmem_base,
                                          int total_tiles, int n_tiles)
 {
-    using E = EpiCfg<BN>;
+    using E = EpiCfg<BN, FAST>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
     const int idx = (warp - 2) >> 2;               // 0..3
@@ -305,11 +331,12 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
     const int row = quad * 32 + lane;
     const Requant rq = make_requant(p.rs, p.relu);
     const float dq = __int_as_float((127 - p.ob) << 23);        // 2^-ob, exact
-    const bool staged = FAST || p.stage_s8;
-    uint32_t acc_phase = 0;
+    const bool staged = FAST;                                    // TMA-stored int8 slabs exist only here
     int it = 0;                                                  // position in this CTA's tile sequence
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        if ((it & (E::kAcc - 1)) != group) continue;
+        if ((it & (E::kGroups - 1)) != group) continue;
+        const int acc = it & (E::kAcc - 1);                      // TMEM accumulator stage of this tile
+        const uint32_t acc_phase = (uint32_t)(it / E::kAcc) & 1u;
         const int m0 = (tile / n_tiles) * kBM, nt0 = (tile % n_tiles) * BN, n0 = nt0 + part * kCols;
         int m = m0 + row, p_img = 0, p_row = 0, p_col = 0;
         bool row_ok = m < p.M;
@@ -336,11 +363,11 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
                     of = p.out_f32 + (size_t)m * p.N + n0;
                 }
             }
-            if (p.out_s8 && !p.stage_s8) o8 = p.out_s8 + (size_t)m * p.N + n0;
+            if (p.out_s8) o8 = p.out_s8 + (size_t)m * p.N + n0;     // generic path: direct int8 stores
         }
-        mbar_wait(tmem_full_bar + group, acc_phase);
+        mbar_wait(tmem_full_bar + acc, acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(group * BN + part * kCols);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kCols);
 
         // one chunk of 16 columns held in registers -> packed int8 (4 words) [+ fp32 / unstaged int8 stores]
         auto emit = [&](const uint32_t (&a)[16], int c0, uint32_t (&packed)[4]) {
@@ -357,97 +384,150 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
                 }
                 return;
             }
+            // generic path, kept compact (the loop body of four chunks must stay I-cache sized): one bias
+            // gather, one requantisation, one strided fp32 store loop that serves NCHW (stride = pixels per
+            // image, lanes = consecutive pixels) and plain [M][N] (stride 1) alike.
+            const int nvalid = p.N - (n0 + c0);            // columns of this chunk inside N (may be <= 0 or > 16)
+            if (nvalid <= 0) return;
             int y[16];
-            const bool full = n0 + c0 + 16 <= p.N;
-            if (full) {
+            if (nvalid >= 16) {
                 const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int4 b4 = __ldg(bp + j);
-                    y[4 * j] = requant_t<POS>((int)a[4 * j], rq, b4.x); y[4 * j + 1] = requant_t<POS>((int)a[4 * j + 1], rq, b4.y);
-                    y[4 * j + 2] = requant_t<POS>((int)a[4 * j + 2], rq, b4.z); y[4 * j + 3] = requant_t<POS>((int)a[4 * j + 3], rq, b4.w);
+                    y[4 * j] = b4.x; y[4 * j + 1] = b4.y; y[4 * j + 2] = b4.z; y[4 * j + 3] = b4.w;
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    y[j] = requant_t<POS>((int)a[j], rq, n0 + c0 + j < p.N ? __ldg(p.bias + n0 + c0 + j) : 0);
+                for (int j = 0; j < 16; ++j) y[j] = j < nvalid ? __ldg(p.bias + n0 + c0 + j) : 0;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)                // the pack saturates from above
+            for (int j = 0; j < 16; ++j) y[j] = min(127, requant_t<POS>((int)a[j], rq, y[j]));
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
                 packed[j] = pack4_sat_s8(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-            if (!(row_ok && n0 + c0 < p.N)) return;
+            if (!row_ok) return;
             if (of) {
-                if (p.hw > 1) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (full || n0 + c0 + j < p.N) of[(size_t)(c0 + j) * cstride] = __fmul_rn((float)min(127, y[j]), dq);
-                } else if (full && (p.N & 3) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<float4 *>(of + c0 + 4 * j) =
-                            make_float4(__fmul_rn((float)min(127, y[4 * j]), dq), __fmul_rn((float)min(127, y[4 * j + 1]), dq),
-                                        __fmul_rn((float)min(127, y[4 * j + 2]), dq), __fmul_rn((float)min(127, y[4 * j + 3]), dq));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (full || n0 + c0 + j < p.N) of[c0 + j] = __fmul_rn((float)min(127, y[j]), dq);
-                }
+                for (int j = 0; j < 16; ++j)
+                    if (j < nvalid) of[(size_t)(c0 + j) * cstride] = __fmul_rn((float)y[j], dq);
             }
             if (o8) {                                  // unstaged fall-back (N % 16 != 0): direct stores
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (full || n0 + c0 + j < p.N) o8[c0 + j] = (int8_t)min(127, y[j]);
+                    if (j < nvalid) o8[c0 + j] = (int8_t)y[j];
             }
         };
 
         // software pipeline over the chunks of the tile: the TMEM load of chunk i+1 is in flight while chunk
-        // i is processed; after each slab (kSlab columns) the warp stages and TMA-stores its 32 rows.
+        // i is processed; after each slab (kSlab columns) the warp stages and TMA-stores its 32 rows.  The
+        // slab loop is NOT unrolled: four warp groups run different tiles, so the code must stay I-cache sized.
         uint32_t a0[16], a1[16];
         uint32_t packed[kChunksPerSlab][4];
         constexpr int kChunks = kCols / 16;
+        static_assert(kChunksPerSlab % 2 == 0 || kSlabs == 1, "chunk parity selects the TMEM register buffer");
         tmem_ld16(taddr, a0);
+#pragma unroll 1
+        for (int slab = 0; slab < kSlabs; ++slab) {
 #pragma unroll
-        for (int ch = 0; ch < kChunks; ++ch) {
-            tmem_ld_wait();
-            if (ch + 1 < kChunks) {
-                if (ch & 1) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), a0);
-                else tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), a1);
-            } else {
-                // every TMEM read of this accumulator has completed: hand it back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_empty_bar + group);
+            for (int j = 0; j < kChunksPerSlab; ++j) {
+                const int ch = slab * kChunksPerSlab + j;
+                tmem_ld_wait();
+                if (ch + 1 < kChunks) {
+                    if (j & 1) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), a0);
+                    else tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), a1);
+                } else {
+                    // every TMEM read of this accumulator has completed: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+                }
+                if (j & 1) emit(a1, ch * 16, packed[j]);
+                else emit(a0, ch * 16, packed[j]);
             }
-            if (ch & 1) emit(a1, ch * 16, packed[ch % kChunksPerSlab]);
-            else emit(a0, ch * 16, packed[ch % kChunksPerSlab]);
-            if (staged && (ch % kChunksPerSlab) == kChunksPerSlab - 1) {
-                const int slab = ch / kChunksPerSlab;
-                const int colb = n0 + slab * kSlab;                     // first output channel of the slab
-                if (colb < p.N) {                                       // warp-uniform
-                    // the previous TMA store of this warp must have finished reading the staging buffer
-                    if (lane == 0) bulk_wait_read0();
-                    __syncwarp();
+            const int colb = n0 + slab * kSlab;                         // first output channel of the slab
+            if (staged && colb < p.N) {                                 // warp-uniform
+                // the previous TMA store of this warp must have finished reading the staging buffer
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < kChunksPerSlab; ++j) {
-                        const uint32_t o = (uint32_t)(lane * kSlab + 16 * j);
-                        *reinterpret_cast<uint4 *>(stage_buf + (o ^ (((o >> 7) & kSwzMask) << 4))) =
-                            make_uint4(packed[j][0], packed[j][1], packed[j][2], packed[j][3]);
-                    }
-                    fence_proxy_async();
+                for (int j = 0; j < kChunksPerSlab; ++j) {
+                    const uint32_t o = (uint32_t)(lane * kSlab + 16 * j);
+                    *reinterpret_cast<uint4 *>(stage_buf + (o ^ (((o >> 7) & kSwzMask) << 4))) =
+                        make_uint4(packed[j][0], packed[j][1], packed[j][2], packed[j][3]);
+                }
+                if (ADD) {
+                    // ---- fused NewAdd: second pass over the staged int8 slab with a transposed mapping -- 8
+                    // lanes per row, 8 columns per lane -- so that the shortcut is read and the int16 sum is
+                    // written with fully coalesced 128-byte row segments; the int8 result replaces y in place.
                     __syncwarp();
-                    if (lane == 0) {
-                        if (p.a_im2col == 2) {     // 32 tile rows = a (32 / TW) x min(TW, 32) piece of the patch
-                            const int r0 = quad * 32;
-                            tma_store_4d(tmap_o, stage_buf, colb, p_col + (r0 & (p.TW - 1)), p_row + (r0 >> p.tw_shift), p_img);
+                    const int u = lane & 7, r4 = lane >> 3;
+                    const int cmul = 1 << p.add_cshift, smul = 1 << p.add_sshift;
+                    const int d = p.add_qshift < 0 ? -p.add_qshift : 0, rc = d ? (1 << (d - 1)) - 1 : 0;
+                    const bool col_ok = colb + 8 * u < p.N;
+#pragma unroll 2
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + r4;
+                        const int gm = m0 + quad * 32 + r;
+                        const uint32_t o = (uint32_t)(r * kSlab + 8 * u);
+                        uint2 *yp = reinterpret_cast<uint2 *>(stage_buf + (o ^ (((o >> 7) & kSwzMask) << 4)));
+                        if (!(col_ok && gm < p.M)) continue;
+                        const size_t e = (size_t)gm * p.N + colb + 8 * u;
+                        int sc[8];
+                        if (p.add_is16) {
+                            const uint4 w = ldg_nc_u4(reinterpret_cast<const int16_t *>(p.add_sc) + e);
+                            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { sc[2 * j] = prmt_sx(ww[j], 0x9910u); sc[2 * j + 1] = prmt_sx(ww[j], 0xbb32u); }
                         } else {
-                            tma_store_2d(tmap_o, stage_buf, colb, m0 + quad * 32);
+                            const uint2 w = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const int8_t *>(p.add_sc) + e));
+                            const uint32_t ww[2] = {w.x, w.y};
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                sc[4 * j] = prmt_sx(ww[j], 0x8880u); sc[4 * j + 1] = prmt_sx(ww[j], 0x9991u);
+                                sc[4 * j + 2] = prmt_sx(ww[j], 0xaaa2u); sc[4 * j + 3] = prmt_sx(ww[j], 0xbbb3u);
+                            }
                         }
-                        bulk_commit();
+                        const uint2 yb = *yp;
+                        const uint32_t yw[2] = {yb.x, yb.y};
+                        int num[8];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            num[4 * j] = prmt_sx(yw[j], 0x8880u); num[4 * j + 1] = prmt_sx(yw[j], 0x9991u);
+                            num[4 * j + 2] = prmt_sx(yw[j], 0xaaa2u); num[4 * j + 3] = prmt_sx(yw[j], 0xbbb3u);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int sv = p.add_sc_relu ? max(sc[j], 0) : sc[j];
+                            num[j] = max(p.add_lo, min(p.add_hi, num[j] * cmul + sv * smul));
+                        }
+                        if (p.out16)
+                            *reinterpret_cast<uint4 *>(p.out16 + e) =
+                                make_uint4(__byte_perm((uint32_t)num[0], (uint32_t)num[1], 0x5410), __byte_perm((uint32_t)num[2], (uint32_t)num[3], 0x5410),
+                                           __byte_perm((uint32_t)num[4], (uint32_t)num[5], 0x5410), __byte_perm((uint32_t)num[6], (uint32_t)num[7], 0x5410));
+                        if (d) {                       // ties to even; the pack saturates
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) num[j] = (num[j] + rc + ((num[j] >> d) & 1)) >> d;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) num[j] = max(-128, min(127, num[j])) << p.add_qshift;
+                        }
+                        *yp = make_uint2(pack4_sat_s8(num[0], num[1], num[2], num[3]), pack4_sat_s8(num[4], num[5], num[6], num[7]));
                     }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (p.a_im2col == 2) {         // 32 tile rows = a (32 / TW) x min(TW, 32) piece of the patch
+                        const int r0 = quad * 32;
+                        tma_store_4d(tmap_o, stage_buf, colb, p_col + (r0 & (p.TW - 1)), p_row + (r0 >> p.tw_shift), p_img);
+                    } else {
+                        tma_store_2d(tmap_o, stage_buf, colb, m0 + quad * 32);
+                    }
+                    bulk_commit();
                 }
             }
         }
-        acc_phase ^= 1;
     }
     if (staged && lane == 0) bulk_wait_read0();
 }
@@ -468,10 +548,11 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t *tmem_full_bar = empty_bar + STAGES;      // [kAcc]
     uint64_t *tmem_empty_bar = tmem_full_bar + 4;      // [kAcc]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 4);
-    constexpr int kAcc = EpiCfg<BN>::kAcc;
+    const bool fast_epi = p.stage_s8 && !p.out_f32;                    // which epilogue configuration runs
+    const int kAcc = fast_epi ? EpiCfg<BN, true>::kAcc : EpiCfg<BN, false>::kAcc;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t kTmemCols = EpiCfg<BN>::kTmemCols;
+    constexpr uint32_t kTmemCols = EpiCfg<BN, true>::kTmemCols;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int total_tiles = (p.a_im2col == 2 ? p.M / kBM : (p.M + kBM - 1) / kBM) * n_tiles;   // mode 2: M = patches * 128
 
@@ -480,7 +561,8 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         if (p.stage_s8) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int s = 0; s < kAcc; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, EpiCfg<BN>::kWarpsPerAcc); }
+        const int arrivals = fast_epi ? EpiCfg<BN, true>::kWarpsPerAcc : EpiCfg<BN, false>::kWarpsPerAcc;
+        for (int s = 0; s < kAcc; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, arrivals); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -561,12 +643,14 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ===================== epilogue (warps 2..17) =====================
         // compile-time variants: POS = right shift by rs >= 1 (the usual case), FAST = int8 output only,
         // leaving through the staged TMA store (the int8 pipeline); anything else takes the generic body
-        const bool fast = p.stage_s8 && !p.out_f32;
+        const bool fast = fast_epi;
         if (p.rs >= 1) {
-            if (fast) epilogue<BN, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            if (fast && p.add_sc) epilogue<BN, true, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else if (fast) epilogue<BN, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else epilogue<BN, true, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
         } else {
-            if (fast) epilogue<BN, false, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            if (fast && p.add_sc) epilogue<BN, false, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else if (fast) epilogue<BN, false, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else epilogue<BN, false, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
         }
     }
@@ -610,17 +694,18 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
     const int n_tiles = (p.N + BN - 1) / BN;
     uint8_t *smem_b = smem;                                              // [n_tiles][R][64 filters][64 B], 64B swizzle
     uint8_t *smem_o = smem_b + (size_t)n_tiles * p.R * (BN * BK);       // warp-private output slabs, 1024-byte aligned
-    uint8_t *smem_a = smem_o + kEpiWarps * EpiCfg<BN>::kSlabBytes;       // ring of raw input rows
+    uint8_t *smem_a = smem_o + kEpiWarps * EpiCfg<BN, true>::kSlabBytes; // ring of raw input rows
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_a + (size_t)rp.stages * rp.a_stage);
     uint64_t *empty_bar = full_bar + kMaxStages;
     uint64_t *tmem_full_bar = empty_bar + kMaxStages;
     uint64_t *tmem_empty_bar = tmem_full_bar + 4;
     uint64_t *b_bar = tmem_empty_bar + 4;
-    constexpr int kAcc = EpiCfg<BN>::kAcc;
+    const bool fast_epi = p.stage_s8 && !p.out_f32;
+    const int kAcc = fast_epi ? EpiCfg<BN, true>::kAcc : EpiCfg<BN, false>::kAcc;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t kTmemCols = EpiCfg<BN>::kTmemCols;
+    constexpr uint32_t kTmemCols = EpiCfg<BN, true>::kTmemCols;
     const int total_tiles = (p.M / kBM) * n_tiles;
     const int per_img = p.tiles_p * p.tiles_q;
 
@@ -628,7 +713,8 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
         for (int s = 0; s < rp.stages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int s = 0; s < kAcc; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, EpiCfg<BN>::kWarpsPerAcc); }
+        const int arrivals = fast_epi ? EpiCfg<BN, true>::kWarpsPerAcc : EpiCfg<BN, false>::kWarpsPerAcc;
+        for (int s = 0; s < kAcc; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, arrivals); }
         mbar_init(b_bar, 1);
         fence_barrier_init();
     }
@@ -686,7 +772,7 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
             }
         }
     } else {
-        const bool fast = p.stage_s8 && !p.out_f32;
+        const bool fast = fast_epi;
         if (p.rs >= 1) {
             if (fast) epilogue<BN, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else epilogue<BN, true, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
@@ -807,8 +893,8 @@ int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, 
     // int8 output tile: [128 rows][min(BN, 128) bytes] boxes of the row-major [M][N] result
     CUtensorMap to = {};
     p.stage_s8 = 0;
-    if (p.out_s8 && (p.N & 15) == 0 && (((uintptr_t)p.out_s8) & 15) == 0) {
-        constexpr int kSlab = pq::EpiCfg<BN>::kSlab;       // each epilogue warp stores [32 rows][kSlab bytes] boxes
+    if (p.out_s8 && !p.out_f32 && (p.N & 15) == 0 && (((uintptr_t)p.out_s8) & 15) == 0) {
+        constexpr int kSlab = pq::EpiCfg<BN, true>::kSlab;     // each epilogue warp stores [32 rows][kSlab bytes] boxes
         int rc;
         if (p.a_im2col == 2) {                     // NHWC output addressed by (channel, q, p, image): TH x TW patches
             const cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.Q, (cuuint64_t)p.P,
@@ -862,8 +948,26 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, int 
 
 }  // namespace
 
-extern "C" int pq_gemm_s8_ex(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs,
-                             int ob, int hw, int flags, float *out_f32, int8_t *out_s8, pq_stream_t stream);
+namespace {
+// validates a fused-add request and copies it into the kernel parameters
+int apply_add(pq::GemmParams &p, const pq_add_desc *add, int conv_ob)
+{
+    if (!add) return PQ_OK;
+    if (!add->shortcut || !add->out8 || p.out_f32 || p.relu) return PQ_EINVAL;
+    if ((p.N & 15) || (((uintptr_t)add->shortcut | (uintptr_t)add->out8 | (uintptr_t)add->out16) & 15)) return PQ_EALIGN;
+    const int o_bit = conv_ob > add->shortcut_bit ? conv_ob : add->shortcut_bit;
+    const int span = o_bit - (conv_ob < add->shortcut_bit ? conv_ob : add->shortcut_bit);
+    if (span > 7 || o_bit < 0 || o_bit > 7 || add->q_bit - o_bit > 15 || o_bit - add->q_bit > 15) return PQ_EUNSUPPORTED;
+    p.add_sc = add->shortcut; p.add_is16 = add->shortcut_is16; p.add_sc_relu = add->shortcut_relu;
+    p.add_cshift = o_bit - conv_ob; p.add_sshift = o_bit - add->shortcut_bit;
+    p.add_lo = add->out_relu ? 0 : -128 * (1 << o_bit); p.add_hi = 127 * (1 << o_bit);
+    p.add_qshift = add->q_bit - o_bit;
+    p.out16 = add->out16; p.out_s8 = add->out8;
+    return PQ_OK;
+}
+int gemm_impl(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs, int ob, int hw,
+              int flags, float *out_f32, int8_t *out_s8, const pq_add_desc *add, pq_stream_t stream);
+}  // namespace
 
 extern "C" int pq_gemm_s8(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs,
                           int ob, int hw, float *out_f32, int8_t *out_s8, pq_stream_t stream)
@@ -874,6 +978,20 @@ extern "C" int pq_gemm_s8(const int8_t *a, const int8_t *w, const int32_t *bias_
 extern "C" int pq_gemm_s8_ex(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs,
                              int ob, int hw, int flags, float *out_f32, int8_t *out_s8, pq_stream_t stream)
 {
+    return gemm_impl(a, w, bias_q, M, N, K, rs, ob, hw, flags, out_f32, out_s8, nullptr, stream);
+}
+
+extern "C" int pq_gemm_s8_add(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs,
+                              int ob, const pq_add_desc *add_host, pq_stream_t stream)
+{
+    if (!add_host) return PQ_EINVAL;
+    return gemm_impl(a, w, bias_q, M, N, K, rs, ob, 1, 0, nullptr, add_host->out8, add_host, stream);
+}
+
+namespace {
+int gemm_impl(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs, int ob, int hw,
+              int flags, float *out_f32, int8_t *out_s8, const pq_add_desc *add, pq_stream_t stream)
+{
     if (M <= 0 || N <= 0 || K <= 0 || hw <= 0) return PQ_EINVAL;
     if (!a || !w || !bias_q || (!out_f32 && !out_s8)) return PQ_EINVAL;
     if ((K & 15) || (((uintptr_t)a | (uintptr_t)w) & 15)) return PQ_EALIGN;
@@ -882,7 +1000,8 @@ extern "C" int pq_gemm_s8_ex(const int8_t *a, const int8_t *w, const int32_t *bi
     int rc = load_driver_entry_points();
     if (rc != PQ_OK) return rc;
     const int bk = K >= 128 ? 128 : (K >= 64 ? 64 : 32);
-    const int bn = pick_bn(M, N);
+    int bn = pick_bn(M, N);
+    if (add && bn < 64) bn = 64;                 // the fused-add pass works on 64-column slabs
     CUtensorMap ta, tb;
     if ((rc = encode_2d(&ta, a, K, M, K, bk, pq::kBM)) != PQ_OK) return rc;
     if ((rc = encode_2d(&tb, w, K, N, K, bk, bn)) != PQ_OK) return rc;
@@ -890,8 +1009,10 @@ extern "C" int pq_gemm_s8_ex(const int8_t *a, const int8_t *w, const int32_t *bi
     p.M = M; p.N = N; p.num_kb = (K + bk - 1) / bk; p.a_im2col = 0;
     p.rs = rs; p.ob = ob; p.hw = hw; p.bias = bias_q; p.out_f32 = out_f32; p.out_s8 = out_s8;
     p.relu = flags & PQ_FLAG_RELU;
+    if ((rc = apply_add(p, add, ob)) != PQ_OK) return rc;
     return launch(ta, tb, p, bk, bn, (cudaStream_t)stream);
 }
+}  // namespace
 
 extern "C" int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
                             const pq_conv_desc *desc_host, float *out_f32_nchw, int8_t *out_s8_nhwc,
@@ -900,9 +1021,28 @@ extern "C" int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const in
     return pq_conv2d_s8_ex(x_nhwc, w_krsc, bias_q, desc_host, 0, out_f32_nchw, out_s8_nhwc, stream);
 }
 
+namespace {
+int conv_impl(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q, const pq_conv_desc *desc_host,
+              int flags, float *out_f32_nchw, int8_t *out_s8_nhwc, const pq_add_desc *add, pq_stream_t stream);
+}
+
 extern "C" int pq_conv2d_s8_ex(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
                                const pq_conv_desc *desc_host, int flags, float *out_f32_nchw,
                                int8_t *out_s8_nhwc, pq_stream_t stream)
+{
+    return conv_impl(x_nhwc, w_krsc, bias_q, desc_host, flags, out_f32_nchw, out_s8_nhwc, nullptr, stream);
+}
+
+extern "C" int pq_conv2d_s8_add(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
+                                const pq_conv_desc *desc_host, const pq_add_desc *add_host, pq_stream_t stream)
+{
+    if (!add_host) return PQ_EINVAL;
+    return conv_impl(x_nhwc, w_krsc, bias_q, desc_host, 0, nullptr, add_host->out8, add_host, stream);
+}
+
+namespace {
+int conv_impl(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q, const pq_conv_desc *desc_host,
+              int flags, float *out_f32_nchw, int8_t *out_s8_nhwc, const pq_add_desc *add, pq_stream_t stream)
 {
     if (!x_nhwc || !w_krsc || !bias_q || !desc_host || (!out_f32_nchw && !out_s8_nhwc)) return PQ_EINVAL;
     const pq_conv_desc &d = *desc_host;
@@ -916,13 +1056,14 @@ extern "C" int pq_conv2d_s8_ex(const int8_t *x_nhwc, const int8_t *w_krsc, const
     const long long M = (long long)d.N * d.P * d.Q;
     if (M > 0x7fffffffLL) return PQ_EUNSUPPORTED;
     if (d.R == 1 && d.S == 1 && d.stride_h == 1 && d.stride_w == 1 && d.pad_h == 0 && d.pad_w == 0)
-        return pq_gemm_s8_ex(x_nhwc, w_krsc, bias_q, (int)M, d.K, d.C, d.rs, d.ob, d.P * d.Q, flags, out_f32_nchw,
-                             out_s8_nhwc, stream);                   // 1x1 stride-1: a plain GEMM over NHWC
+        return gemm_impl(x_nhwc, w_krsc, bias_q, (int)M, d.K, d.C, d.rs, d.ob, d.P * d.Q, flags, out_f32_nchw,
+                         out_s8_nhwc, add, stream);                  // 1x1 stride-1: a plain GEMM over NHWC
     if (d.C & 31) return PQ_EUNSUPPORTED;                            // im2col path: channel blocks of >= 32
     int rc = load_driver_entry_points();
     if (rc != PQ_OK) return rc;
     const int bk = (d.C % 128 == 0) ? 128 : ((d.C % 64 == 0) ? 64 : 32);
-    const int bn = pick_bn(M, d.K);
+    int bn = pick_bn(M, d.K);
+    if (add && bn < 64) bn = 64;                 // the fused-add pass works on 64-column slabs
     CUtensorMap ta, tb;
     if ((rc = encode_im2col(&ta, x_nhwc, d, bk)) != PQ_OK) return rc;
     const uint64_t ktot = (uint64_t)d.R * d.S * d.C;
@@ -933,8 +1074,10 @@ extern "C" int pq_conv2d_s8_ex(const int8_t *x_nhwc, const int8_t *w_krsc, const
     p.P = d.P; p.Q = d.Q; p.stride_h = d.stride_h; p.stride_w = d.stride_w; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
     p.rs = d.rs; p.ob = d.ob; p.hw = d.P * d.Q; p.bias = bias_q; p.out_f32 = out_f32_nchw; p.out_s8 = out_s8_nhwc;
     p.relu = flags & PQ_FLAG_RELU;
+    if ((rc = apply_add(p, add, d.ob)) != PQ_OK) return rc;
     return launch(ta, tb, p, bk, bn, (cudaStream_t)stream);
 }
+}  // namespace
 
 // Convolution with <= 8 input channels over a zero-padded NHWC image with 8-byte pixels (see GemmParams):
 // xp is [N][Hp][Wp][8] int8 as written by pq_quantize_nchw_to_padded_nhwc8_s8 (image pixel (h, w) at
@@ -976,7 +1119,7 @@ extern "C" int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const
         const int pitch = Wp * kPix;
         const int tiles_q = (d.Q + pq::kBM - 1) / pq::kBM;
         const int a_stage = (d.R * pitch + 2112 + 1023) / 1024 * 1024;       // + over-read of the last window rows
-        const long long fixed = 1024 + (long long)n_tiles * d.R * 4096 + pq::kEpiWarps * pq::EpiCfg<64>::kSlabBytes + 256;
+        const long long fixed = 1024 + (long long)n_tiles * d.R * 4096 + pq::kEpiWarps * pq::EpiCfg<64, true>::kSlabBytes + 256;
         const long long stages_fit = (227 * 1024 - fixed) / a_stage;
         const long long tiles_m = (long long)d.N * d.P * tiles_q;
         if (stages_fit >= 2 && tiles_m * pq::kBM <= 0x7fffffffLL &&
@@ -991,11 +1134,13 @@ extern "C" int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const
             const uint64_t ktot = (uint64_t)d.R * kBK;
             if ((rc = encode_2d(&tb, w_krs8, ktot, d.K, ktot, kBK, 64)) != PQ_OK) return rc;
             q.stage_s8 = 0;
-            if (q.out_s8 && (q.N & 15) == 0 && (((uintptr_t)q.out_s8) & 15) == 0) {
+            if (q.out_s8 && !q.out_f32 && (q.N & 15) == 0 && (((uintptr_t)q.out_s8) & 15) == 0) {
                 const cuuint64_t odims[4] = {(cuuint64_t)q.N, (cuuint64_t)q.Q, (cuuint64_t)q.P, (cuuint64_t)d.N};
                 const cuuint64_t ostr[3] = {(cuuint64_t)q.N, (cuuint64_t)q.N * q.Q, (cuuint64_t)q.N * q.Q * q.P};
-                const cuuint32_t obox[4] = {64, 32, 1, 1};            // one epilogue warp: 32 output columns x 64 channels
-                if ((rc = encode_nd(&to, q.out_s8, 4, odims, ostr, obox, 64)) != PQ_OK) return rc;
+                // one epilogue warp stores 32 output columns x kSlab channels
+                constexpr int slab = pq::EpiCfg<64, true>::kSlab;
+                const cuuint32_t obox[4] = {(cuuint32_t)slab, 32, 1, 1};
+                if ((rc = encode_nd(&to, q.out_s8, 4, odims, ostr, obox, slab)) != PQ_OK) return rc;
                 q.stage_s8 = 1;
             }
             const size_t smem = (size_t)fixed + (size_t)rp.stages * a_stage;

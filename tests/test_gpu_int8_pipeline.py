@@ -59,6 +59,40 @@ def test_add_requant_exact(abit, bbit, qbit, a16, b16):
         assert np.array_equal(o8.cpu().numpy().astype(np.int64), ref8)
 
 
+# (B, Cin, H, W, Cout, k, stride, pad, conv_ob, shortcut_bit, q_bit, shortcut int16?)
+FUSED_ADD_CASES = [(2, 64, 14, 14, 256, 1, 1, 0, 4, 5, 4, True), (3, 32, 9, 11, 64, 3, 1, 1, 5, 3, 2, False),
+                   (2, 128, 7, 7, 512, 1, 1, 0, 3, 6, 6, True), (1, 64, 20, 20, 32, 3, 2, 1, 6, 6, 7, False),
+                   (2, 256, 5, 5, 1024, 1, 1, 0, 2, 4, 1, True), (2, 16, 33, 17, 48, 1, 1, 0, 4, 4, 4, False)]
+
+
+@pytest.mark.parametrize("case", FUSED_ADD_CASES, ids=["c%d_%dx%d_o%d_k%d" % (c[1], c[2], c[3], c[4], c[5]) for c in FUSED_ADD_CASES])
+def test_conv_add_fused_equals_conv_then_add(case):
+    """pq_conv2d_s8_add / pq_gemm_s8_add (NewConv2d + NewAdd + ReLU in one epilogue) against the two separate
+    kernels, which are pinned to the reference elsewhere."""
+    from common.quantity import _native
+    B, Cin, H, W, Cout, k, stride, pad, ob, sbit, qbit, s16 = case
+    g = torch.Generator(device="cuda").manual_seed(Cin + Cout)
+    x = torch.randint(-128, 128, (B, H, W, Cin), dtype=torch.int8, device="cuda", generator=g)
+    w = torch.randint(-20, 21, (Cout, k, k, Cin), dtype=torch.int8, device="cuda", generator=g)
+    bias = torch.randint(-128, 128, (Cout,), dtype=torch.int32, device="cuda", generator=g)
+    P, Q = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    if s16:
+        lim = 127 * 2 ** sbit
+        sc = torch.randint(-lim - 2 ** sbit, lim + 1, (B, P, Q, Cout), dtype=torch.int16, device="cuda", generator=g)
+    else:
+        sc = torch.randint(-128, 128, (B, P, Q, Cout), dtype=torch.int8, device="cuda", generator=g)
+    rs = 7
+    _, y8 = _native.conv2d_s8(x, w, bias, (stride, stride), (pad, pad), rs, ob, want_f32=False, want_s8=True)
+    for sc_relu, out_relu in ((False, False), (False, True), (True, True)):
+        ref16, ref8 = _native.add_requant(y8, ob, False, sc, sbit, sc_relu, qbit, out_relu=out_relu)
+        o16, o8 = _native.conv2d_s8_add(x, w, bias, (stride, stride), (pad, pad), rs, ob, sc, sbit, sc_relu, qbit, out_relu)
+        assert torch.equal(o16, ref16), (sc_relu, out_relu)
+        assert torch.equal(o8, ref8), (sc_relu, out_relu)
+        _, o8b = _native.conv2d_s8_add(x, w, bias, (stride, stride), (pad, pad), rs, ob, sc, sbit, sc_relu, qbit, out_relu,
+                                       want16=False)
+        assert torch.equal(o8b, ref8)
+
+
 def _build_recon(model_name, tmp_path, batch_shape):
     import tools
     from common.quantity import merge_bn
@@ -74,11 +108,12 @@ def _build_recon(model_name, tmp_path, batch_shape):
         return r.ReconModel(r.get_quantity_information(), None).cuda().eval()
 
 
-@pytest.mark.parametrize("model_name,batch", [("r18", 3), ("r50", 2)])
-def test_pipeline_equals_fp32_boundary_model(tmp_path, model_name, batch):
+@pytest.mark.parametrize("model_name,batch,fuse_add", [("r18", 3, False), ("r50", 2, False), ("r50", 2, True), ("r18", 2, True)])
+def test_pipeline_equals_fp32_boundary_model(tmp_path, monkeypatch, model_name, batch, fuse_add):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from common.quantity import QTensor, enable_int8_pipeline, NewConv2d
+    from common.quantity import QTensor, enable_int8_pipeline, NewConv2d, int8_pipeline
+    monkeypatch.setattr(int8_pipeline, "FUSE_ADD_INTO_CONV", fuse_add)
     model = _build_recon(model_name, tmp_path, batch)
     x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(42)).cuda()
     with torch.no_grad():
@@ -109,6 +144,9 @@ def test_pipeline_equals_fp32_boundary_model(tmp_path, model_name, batch):
                 want = torch.relu(want)          # the ReLU that follows was fused into this epilogue
             assert torch.equal(got, want), name
     assert n_q >= 15
+    from common.quantity import _native
+    if fuse_add:
+        assert _native.LAUNCHES.get("conv_add_s8", 0) > 0, "no NewAdd was fused into its producer convolution"
     # the same forward captured once and replayed as a CUDA graph, on the capture batch and on a new one
     from common.quantity import GraphedForward
     fwd = GraphedForward(model, x)
