@@ -213,7 +213,8 @@ def ours(args):
     K, W = args.steps, max(args.warmup, 3)
 
     # warm-up: W steps through the same job shape (cuDNN autotune, allocator, kernels)
-    warm = [make_batch(10_000 + rank * W + i, device="cuda") for i in range(W)]
+    # (pinned host batches: the warm-up also exercises the copy stream / H2D path the e2e job uses)
+    warm = [make_batch(10_000 + rank * W + i, pin=True) for i in range(W)]
     _, qw = run_job(net, ShardedBatches(warm, W * world, rank, world), W * world, workdir, rank, world)
     del warm
     # Pre-size the caching allocator's pool for the K-batch activation cache so that no cudaMalloc

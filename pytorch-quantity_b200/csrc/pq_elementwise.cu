@@ -260,24 +260,30 @@ quantize_im2col_kernel(const float *__restrict__ x, int8_t *__restrict__ a, int 
 // loads along w, one coalesced 8-byte store.
 __global__ void __launch_bounds__(kEwThreads)
 quantize_pad_nhwc8_kernel(const float *__restrict__ x, uint2 *__restrict__ q, int C, int H, int W, int ph, int pw,
-                          int Hp, int Wp, size_t total, float scale)
+                          int Hp, int Wp, float scale)
 {
+    // grid = (pixel pairs of a padded row, padded rows, images): no integer division anywhere; every thread
+    // converts two horizontally adjacent padded pixels and stores them as one 16-byte vector (Wp is even)
+    const int wp = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (wp >= Wp) return;
+    const int hp = blockIdx.y;
+    const size_t n = blockIdx.z;
+    const int h = hp - ph;
     const size_t HW = (size_t)H * W;
-    for (size_t t = (size_t)blockIdx.x * kEwThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kEwThreads) {
-        const int wp = (int)(t % Wp);
-        const size_t r = t / Wp;
-        const int hp = (int)(r % Hp);
-        const size_t n = r / Hp;
-        const int h = hp - ph, w = wp - pw;
-        unsigned int word[2] = {0u, 0u};
-        if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) {
-            const float *src = x + (n * C * H + h) * (size_t)W + w;
+    unsigned int word[4] = {0u, 0u, 0u, 0u};
+    if ((unsigned)h < (unsigned)H) {
+        const float *row = x + (n * C * H + h) * (size_t)W;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (c < C) word[c >> 2] |= ((unsigned int)q8i(__ldg(src + c * HW), scale) & 0xffu) << ((c & 3) * 8);
+        for (int k = 0; k < 2; ++k) {
+            const int w = wp + k - pw;
+            if ((unsigned)w < (unsigned)W) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < C) word[2 * k + (c >> 2)] |= ((unsigned int)q8i(__ldg(row + c * HW + w), scale) & 0xffu) << ((c & 3) * 8);
+            }
         }
-        q[t] = make_uint2(word[0], word[1]);
     }
+    *reinterpret_cast<uint4 *>(q + (n * Hp + hp) * (size_t)Wp + wp) = make_uint4(word[0], word[1], word[2], word[3]);
 }
 
 }  // namespace pq
@@ -393,9 +399,11 @@ extern "C" int pq_quantize_nchw_to_padded_nhwc8_s8(const float *x, int8_t *q, in
 {
     if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || pad_h < 0 || pad_w < 0 || !x || !q) return PQ_EINVAL;
     if (C > 8 || Hp < H + pad_h || Wp < W + pad_w || ib < -126 || ib > 126) return PQ_EUNSUPPORTED;
-    if (((unsigned long long)q) & 7ull) return PQ_EALIGN;
-    const size_t total = (size_t)N * Hp * Wp;
-    pq::quantize_pad_nhwc8_kernel<<<ew_grid(total), pq::kEwThreads, 0, (cudaStream_t)stream>>>(
-        x, reinterpret_cast<uint2 *>(q), C, H, W, pad_h, pad_w, Hp, Wp, total, ldexpf(1.0f, ib));
+    if ((((unsigned long long)q) & 15ull) || (Wp & 1)) return PQ_EALIGN;
+    if (Hp > 65535 || N > 65535) return PQ_EUNSUPPORTED;
+    const int threads = Wp / 2 <= 128 ? 128 : pq::kEwThreads;          // a 224-wide image is 115 pixel pairs per row
+    const dim3 grid((unsigned)((Wp / 2 + threads - 1) / threads), (unsigned)Hp, (unsigned)N);
+    pq::quantize_pad_nhwc8_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<uint2 *>(q), C, H, W, pad_h, pad_w, Hp, Wp, ldexpf(1.0f, ib));
     return (int)cudaGetLastError();
 }

@@ -214,8 +214,15 @@ class Quantity(object):
                 return i, img, None
             if copy_stream is None:
                 copy_stream = torch.cuda.Stream(dev)
+            # The buffer comes from the compute stream's allocator pool (no cudaMalloc once the pool is warm);
+            # the copy stream may touch it only after everything already queued on the compute stream.
+            main = torch.cuda.current_stream(dev)
+            staged = torch.empty(img.shape, dtype=img.dtype, device=dev)
+            ready = torch.cuda.Event()
+            ready.record(main)
             with torch.cuda.stream(copy_stream):
-                staged = img.to(dev, non_blocking=True)
+                copy_stream.wait_event(ready)
+                staged.copy_(img, non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(copy_stream)
             return i, staged, done
@@ -232,9 +239,7 @@ class Quantity(object):
     def _claim(self, staged):
         i, img, done = staged
         if done is not None:
-            cur = torch.cuda.current_stream(self.cuda_device)
-            cur.wait_event(done)
-            img.record_stream(cur)
+            torch.cuda.current_stream(self.cuda_device).wait_event(done)
         return i, img
 
     # --------------------------------------------------------------- activation hooks
