@@ -1,5 +1,9 @@
+"""Development experiment: fp32 forward of the calibration model under layout / graph / TF32 variants
+(NCHW 17.2 ms, channels_last 21.1 ms, CUDA graph 16.7 ms, TF32 6.6 ms on B200, batch 64)."""
 import sys, os, time
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pytorch-quantity_b200"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "pytorch-quantity_b200"))
 import torch
 from bench import build_model
 torch.backends.cudnn.allow_tf32 = False

@@ -22,6 +22,13 @@ echo "gemm 3x3 rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_s8_kernel -s 3 -c 1 \
     -f -o gpurun_out/prof_gemm_s8_conv1x1_64to256x56 python bench_conv_layers.py --s8-out --only 3 > gpurun_out/ncu_gemm2.log 2>&1
 echo "gemm 1x1 rc=$?"
+# the stem row kernel and the int8-pipeline add kernel
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_rows_s8_kernel -s 3 -c 1 \
+    -f -o gpurun_out/prof_conv_rows_stem python bench_conv_layers.py --s8-out --only 0 > gpurun_out/ncu_rows.log 2>&1
+echo "rows rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:add_requant_kernel -s 20 -c 1 \
+    -f -o gpurun_out/prof_add_requant python bench_sim.py --mode model --iters 1 > gpurun_out/ncu_add.log 2>&1
+echo "add rc=$?"
 ls -la gpurun_out/*.ncu-rep
 unset PQ_BENCH_NO_AUTOTUNE
-timeout 300 python gpurun_exp_fwd.py > gpurun_out/exp_fwd.txt 2>&1; cat gpurun_out/exp_fwd.txt | tail -6
+timeout 300 python scripts/exp_forward_variants.py > gpurun_out/exp_fwd.txt 2>&1; cat gpurun_out/exp_fwd.txt | tail -6
