@@ -55,6 +55,16 @@ const char *pq_error_string(int code);
 int pq_absmax_multi_f32(const float *const *xs_host, const uint64_t *ns_host, int k,
                         uint32_t *max_bits, pq_stream_t stream);
 
+/* ---- extension of a1 (north_star: "per-channel and per-tensor max-abs"): the reference only ever
+ * reduces per tensor (distribution_collector.py:77, tools/pytorch_quantizer.py:639,651), so this entry
+ * point has no reference counterpart; its contract is the same reduction taken per channel.
+ * x is a contiguous fp32 [outer][channels][inner] tensor (NCHW activations: outer = N, inner = H*W;
+ * a weight [K][C][R][S] per output channel: outer = 1, channels = K, inner = C*R*S):
+ *   max_bits[c] = max(max_bits[c], bits(max |x[:, c, :]|)),  uint32 pattern as in pq_absmax_multi_f32.
+ * Requires channels <= 8192, inner < 2^31 - 2^14 and outer * channels < 2^31. */
+int pq_absmax_per_channel_f32(const float *x, uint64_t outer, int channels, uint64_t inner,
+                              uint32_t *max_bits, pq_stream_t stream);
+
 /* ---- a3: DistributionCollector._add_to_distribution, distribution_collector.py:127-135
  * for every x != 0:  hist[i][min((int)trunc(fl32(|x| / interval_i)), 2047)] += 1
  * with a correctly rounded fp32 division.  hist is int64 [k][2048] (the reference's int32
@@ -185,6 +195,25 @@ int pq_add_requant(const void *a, int a_is16, int a_bit, int a_relu, const void 
 int pq_add_requant_ex(const void *a, int a_is16, int a_bit, int a_relu, const void *b, int b_is16, int b_bit,
                       int b_relu, size_t n, int flags, int16_t *out16, int8_t *out8, int q_bit,
                       pq_stream_t stream);
+
+/* Concat (fabu_layer.py:14-20, left in place by tools/reconstruction.py:219-238) followed by the
+ * consumer's input quantiser Quantity(q_bit) (new_quantity_op.py:48-58), on quantised operands: source i is
+ * int8 or int16 [pixels][channels_i] (NHWC, channel-last) holding v / 2^bit_i; the output is int8
+ * [pixels][c_out_pad] with the sources side by side along the channel axis,
+ *   out[p][off_i + c] = clamp(round_half_even(relu_i?(v) * 2^(q_bit - bit_i)), -128, 127),
+ * which is exactly Quantity(q_bit)(torch.cat(de-quantised sources, 1)) because every product is an exact
+ * fp32 value.  Channels sum(channels_i) .. c_out_pad-1 are zero-filled (tensor-core channel padding).
+ * srcs_host is a HOST array of k <= PQ_CONCAT_MAX_SOURCES descriptors; |q_bit - bit_i| <= 15. */
+#define PQ_CONCAT_MAX_SOURCES 8
+typedef struct pq_concat_src {
+    const void *ptr;
+    int is16;                /* int16 payload (the exact sum of an Eltwise) instead of int8 */
+    int channels;
+    int bit;
+    int relu;                /* apply max(., 0) on load (a pending nn.ReLU) */
+} pq_concat_src;
+int pq_concat_requant_s8(const pq_concat_src *srcs_host, int k, size_t pixels, int q_bit, int c_out_pad,
+                         int8_t *out, pq_stream_t stream);
 
 /* NewConv2d + NewAdd (+ the nn.ReLU after the Eltwise) in ONE kernel: the conv / GEMM epilogue adds the
  * shortcut operand and writes the exact int16 sum and its int8 requantisation, exactly as pq_add_requant_ex

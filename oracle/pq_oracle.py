@@ -85,6 +85,16 @@ def absmax_c(x, cur=0.0):
     return out[0]
 
 
+def absmax_per_channel(x, channel_dim=1, cur=None):
+    """Extension of a1 with NO reference counterpart (the reference reduces per tensor only,
+    cq/distribution_collector.py:77): the same ``max(|max x|, |min x|)`` taken per channel.
+    Parity for it is therefore unpinned by the reference; this numpy statement is its contract."""
+    x = np.asarray(x, dtype=np.float32)
+    axes = tuple(a for a in range(x.ndim) if a != channel_dim % x.ndim)
+    m = np.maximum(np.abs(x.max(axis=axes)), np.abs(x.min(axis=axes))).astype(np.float32)
+    return m if cur is None else np.maximum(np.asarray(cur, dtype=np.float32), m)
+
+
 # --------------------------------------------------------------------------- a2
 def interval(max_val, statistic=1, interval_num=INTERVAL_NUM):
     """cq/distribution_collector.py:60-61 under numpy 2: np.float32 when max_val is
@@ -178,6 +188,12 @@ def quantize_input(x, ib):
     """cq/new_quantity_op.py:48-58 -> integer-valued float32."""
     x = np.asarray(x, dtype=np.float32)
     return np.clip(np.rint(x * np.float32(2.0 ** ib)), -128.0, 127.0).astype(np.float32)
+
+
+def concat_quantize(parts, ib, dim=1):
+    """Concat (cq/fabu_layer.py:14-20; tools/reconstruction.py:219-238 leaves it in fp32) followed by
+    the consuming layer's input quantiser (cq/new_quantity_op.py:48-58)."""
+    return quantize_input(np.concatenate([np.asarray(p, dtype=np.float32) for p in parts], axis=dim), ib)
 
 
 # --------------------------------------------------------------------------- a14

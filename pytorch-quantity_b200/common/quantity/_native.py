@@ -25,6 +25,7 @@ SYMBOLS = {
     "pq_version": (_i, []),
     "pq_error_string": (ctypes.c_char_p, [_i]),
     "pq_absmax_multi_f32": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "pq_absmax_per_channel_f32": (_i, [_vp, ctypes.c_uint64, _i, ctypes.c_uint64, _vp, _vp]),
     "pq_hist2048_multi_f32": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "pq_kl_workspace_doubles": (_sz, []),
     "pq_kl_search_f64": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
@@ -46,6 +47,7 @@ SYMBOLS = {
     "pq_maxpool_nhwc_s8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pq_add_requant": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _sz, _vp, _vp, _i, _vp]),
     "pq_add_requant_ex": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _sz, _i, _vp, _vp, _i, _vp]),
+    "pq_concat_requant_s8": (_i, [_vp, _i, _sz, _i, _i, _vp, _vp]),
 }
 FLAG_RELU = 1
 
@@ -63,6 +65,14 @@ class AddDesc(ctypes.Structure):
                 ("shortcut_relu", ctypes.c_int), ("out_relu", ctypes.c_int), ("q_bit", ctypes.c_int),
                 ("out16", ctypes.c_void_p), ("out8", ctypes.c_void_p)]
 
+
+class ConcatSrc(ctypes.Structure):
+    """struct pq_concat_src"""
+    _fields_ = [("ptr", ctypes.c_void_p), ("is16", ctypes.c_int), ("channels", ctypes.c_int),
+                ("bit", ctypes.c_int), ("relu", ctypes.c_int)]
+
+
+CONCAT_MAX_SOURCES = 8
 
 _lib = None
 
@@ -161,6 +171,24 @@ def absmax_multi(tensors, max_bits):
         with _Timed("absmax", 1, 4 * sum(t.numel() for t in part), max_bits.device):
             check(lib().pq_absmax_multi_f32(ptrs, ns, len(part), out.data_ptr(), _stream(max_bits)),
                   "pq_absmax_multi_f32")
+
+
+def absmax_per_channel(x, max_bits, channel_dim=1):
+    """max_bits (int32 CUDA [C]) |= bit pattern of max |x| over every axis but `channel_dim` of the
+    contiguous fp32 CUDA tensor x (extension of a1; see include/pq_sm100.h)."""
+    require_cuda(x, "absmax_per_channel")
+    if x.dtype != torch.float32:
+        raise RuntimeError("fp32 expected, got %s" % x.dtype)
+    xc = x.detach().contiguous()
+    shape = tuple(xc.shape)
+    channel_dim %= len(shape)
+    outer = int(np.prod(shape[:channel_dim], dtype=np.int64))
+    inner = int(np.prod(shape[channel_dim + 1:], dtype=np.int64))
+    C = shape[channel_dim]
+    assert max_bits.dtype == torch.int32 and max_bits.numel() >= C and max_bits.is_contiguous()
+    with _Timed("absmax_channel", 1, 4 * xc.numel(), xc.device):
+        check(lib().pq_absmax_per_channel_f32(xc.data_ptr() if xc.numel() else None, outer, C, inner,
+                                              max_bits.data_ptr(), _stream(xc)), "pq_absmax_per_channel_f32")
 
 
 def hist_multi(tensors, intervals, hist):
@@ -392,3 +420,27 @@ def add_requant(a, a_bit, a_relu, b, b_bit, b_relu, q_bit, want16=True, want8=Tr
                                       out16.data_ptr() if want16 else None, out8.data_ptr() if want8 else None,
                                       int(q_bit), _stream(a)), "pq_add_requant_ex")
     return out16, out8
+
+
+def concat_requant_s8(sources, q_bit, c_out_pad=None):
+    """Concat along channels + Quantity(q_bit) on quantised NHWC payloads.  sources: list of
+    (payload int8 / int16 [N][H][W][C_i], bit, relu).  Returns int8 [N][H][W][c_out_pad]."""
+    first = sources[0][0]
+    require_cuda(first, "concat_requant_s8")
+    N, H, W = first.shape[:3]
+    k = len(sources)
+    if k > CONCAT_MAX_SOURCES:
+        raise RuntimeError("concat_requant_s8: at most %d sources" % CONCAT_MAX_SOURCES)
+    arr = (ConcatSrc * k)()
+    c_sum = nbytes = 0
+    for i, (t, bit, relu) in enumerate(sources):
+        assert t.is_contiguous() and tuple(t.shape[:3]) == (N, H, W) and t.dtype in (torch.int8, torch.int16)
+        arr[i] = ConcatSrc(t.data_ptr(), 1 if t.dtype == torch.int16 else 0, t.shape[3], int(bit), 1 if relu else 0)
+        c_sum += t.shape[3]
+        nbytes += t.numel() * t.element_size()
+    c_out_pad = c_sum if c_out_pad is None else c_out_pad
+    out = torch.empty((N, H, W, c_out_pad), dtype=torch.int8, device=first.device)
+    with _Timed("concat_requant", 1, nbytes + out.numel(), first.device):
+        check(lib().pq_concat_requant_s8(arr, k, N * H * W, int(q_bit), c_out_pad, out.data_ptr(), _stream(first)),
+              "pq_concat_requant_s8")
+    return out

@@ -118,6 +118,37 @@ class DistributionCollector:
         _native.hist_multi(flat, intervals, self._hist)
         self._hist_dirty = True
 
+    # ------------------------------------------- per-channel maxima (extension; no reference counterpart)
+    def refresh_channel_max_val(self, tensors, channel_dim=1):
+        """Running max |x| per channel of every listed tensor that has a channel axis (north_star item 1,
+        "per-channel and per-tensor max-abs").  The reference reduces per tensor only
+        (distribution_collector.py:77); this is the same reduction kept per channel, one
+        pq_absmax_per_channel_f32 launch per tensor, state int32 bit patterns on the device."""
+        if not hasattr(self, "_chan_bits"):
+            self._chan_bits = {}
+        for name in self._tensor_list:
+            x = tensors[name]
+            if not (isinstance(x, torch.Tensor) and x.is_cuda):
+                x = _native.to_device_f32(x, self._device).view(np.shape(tensors[name]))
+            if x.dim() <= channel_dim:
+                continue
+            if name not in self._chan_bits:
+                self._chan_bits[name] = torch.zeros(x.shape[channel_dim], dtype=torch.int32, device=x.device)
+            _native.absmax_per_channel(x.float(), self._chan_bits[name], channel_dim)
+
+    @property
+    def channel_max_vals(self):
+        """dict name -> np.float32 [C] (one D2H per tensor)."""
+        assert hasattr(self, "_chan_bits"), "Please use refresh_channel_max_val() first."
+        return {name: b.view(torch.float32).cpu().numpy() for name, b in self._chan_bits.items()}
+
+    def all_reduce_channel_max(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            for name in self._tensor_list:
+                if name in getattr(self, "_chan_bits", {}):
+                    dist.all_reduce(self._chan_bits[name], op=dist.ReduceOp.MAX, group=group)
+
     # ------------------------------------------------------- multi-GPU merge (new; SURVEY 8e)
     def device_state(self):
         """(max_bits int32 [n], hist int64 [n][2048]) on the device."""

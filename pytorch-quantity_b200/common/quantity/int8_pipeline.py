@@ -11,7 +11,10 @@ layers hand each other int8 NHWC payloads wrapped in a lazy ``QTensor``:
     NewAdd(QTensor, QTensor)                        exact integer sum: int16 (for the next identity
                                                     shortcut) + int8 at the Eltwise's feat bit (for convs);
                                                     evaluated lazily so that a following nn.ReLU is fused
-    anything else (AvgPool2d, Concat, user code)    the QTensor de-quantises itself to fp32 NCHW first
+    Concat(QTensor, QTensor) / torch.cat(dim=1)     lazy: the consuming NewConv2d asks for the concatenation at
+                                                    ITS input bit and one bandwidth kernel (pq_concat_requant_s8)
+                                                    writes the channel-padded int8 NHWC operand directly
+    anything else (AvgPool2d, user code)            the QTensor de-quantises itself to fp32 NCHW first
 
 so the final output is bit-identical to the fp32-boundary model while HBM traffic drops ~4x.
 ``enable_int8_pipeline(model)`` turns it on for a model built by ``Reconstruction.ReconModel``.
@@ -82,6 +85,40 @@ class _LazyAdd:
         return self.done[relu]
 
 
+class _LazyCat:
+    """torch.cat(members, 1) that has not run yet.  The reference leaves Concat in fp32
+    (tools/reconstruction.py:219-238) and the consumer's Quantity(ib) quantises the result, so the exact
+    int8 operand is ``clamp(rint(member * 2^ib))`` per member -- computed here from the members' most
+    exact integer payloads once the consumer (and so ib and its channel padding) is known."""
+
+    def __init__(self, members):
+        self.members = []                              # (QTensor, extra_relu), nested concatenations flattened
+        for m in members:
+            if m._lazy_cat is not None:
+                self.members += [(t, r or m.relu_pending) for t, r in m._lazy_cat.members]
+            else:
+                self.members.append((m, False))
+        self.done = {}
+
+    def supported(self, q_bit):
+        return len(self.members) <= _native.CONCAT_MAX_SOURCES and all(
+            t.exact_bit() is not None and abs(q_bit - t.exact_bit()) <= 15 for t, _ in self.members)
+
+    def get(self, q_bit, c_pad, relu):
+        key = (q_bit, c_pad, relu)
+        if key not in self.done:
+            srcs = []
+            for t, extra in self.members:
+                payload, bit, r = _operand(t)
+                srcs.append((payload, bit, r or extra or relu))
+            self.done[key] = _native.concat_requant_s8(srcs, q_bit, c_pad)
+        return self.done[key]
+
+    def dequantize(self):
+        parts = [torch.relu(t.dequantize()) if extra else t.dequantize() for t, extra in self.members]
+        return torch.cat(parts, 1)
+
+
 class QTensor(torch.Tensor):
     """A float32 NCHW tensor that exists only as quantised payloads until somebody needs the floats."""
 
@@ -91,13 +128,14 @@ class QTensor(torch.Tensor):
                                                    requires_grad=False)
 
     def __init__(self, shape, device, q8=None, q8_bit=None, s16=None, s16_bit=None, relu_pending=False,
-                 nonneg=False, lazy=None, lazy_conv=None):
+                 nonneg=False, lazy=None, lazy_conv=None, lazy_cat=None):
         self._q8, self.q8_bit = q8, q8_bit             # int8 NHWC, value = q8 / 2^q8_bit (after pending relu)
         self._s16, self.s16_bit = s16, s16_bit         # int16 NHWC exact value (outputs of NewAdd)
         self.relu_pending = relu_pending               # a ReLU was applied logically but not to the payloads
         self.nonneg = nonneg                           # payloads are already >= 0
         self._lazy = lazy                              # _LazyAdd: payloads appear on first use
         self._lazy_conv = lazy_conv                    # _LazyConv: the int8 payload appears on first use
+        self._lazy_cat = lazy_cat                      # _LazyCat: payload exists per (consumer bit, padding)
         self._q8_relu = None
 
     def exact_bit(self):
@@ -140,6 +178,9 @@ class QTensor(torch.Tensor):
 
     def dequantize(self):
         """fp32 NCHW, exactly what the fp32-boundary model would hold here (cold path: plain torch ops)."""
+        if self._lazy_cat is not None:
+            v = self._lazy_cat.dequantize()
+            return torch.relu(v) if self.relu_pending else v
         self._materialize()
         if self.s16 is not None:
             v = self.s16.to(torch.float32) * (2.0 ** -self.s16_bit)
@@ -153,7 +194,8 @@ class QTensor(torch.Tensor):
         if self.nonneg:
             return self
         return QTensor(self.shape, self.device, q8=self._q8, q8_bit=self.q8_bit, s16=self._s16,
-                       s16_bit=self.s16_bit, relu_pending=True, lazy=self._lazy, lazy_conv=self._lazy_conv)
+                       s16_bit=self.s16_bit, relu_pending=True, lazy=self._lazy, lazy_conv=self._lazy_conv,
+                       lazy_cat=self._lazy_cat)
 
     # ---- dispatch -------------------------------------------------------------------------
     @classmethod
@@ -167,6 +209,10 @@ class QTensor(torch.Tensor):
         if func in (F.relu, torch.relu, torch.Tensor.relu) and isinstance(args[0], QTensor) \
                 and not kwargs.get("inplace", False) and len(args) == 1:
             return args[0].with_relu()
+        if func is torch.cat:
+            out = _concat(*args, **kwargs)
+            if out is not None:
+                return out
         if func is F.max_pool2d and isinstance(args[0], QTensor):
             out = _maxpool(args[0], *args[1:], **kwargs)
             if out is not None:
@@ -196,6 +242,24 @@ def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
 
+def _concat(tensors, dim=0, out=None):
+    """torch.cat of QTensors along the channel axis stays quantised (lazily, see _LazyCat)."""
+    if out is not None or dim not in (1, -3) or not isinstance(tensors, (list, tuple)) or len(tensors) < 1:
+        return None
+    if not all(isinstance(t, QTensor) and t.dim() == 4 for t in tensors):
+        return None
+    first = tensors[0]
+    if any(t.shape[0] != first.shape[0] or t.shape[2:] != first.shape[2:] for t in tensors):
+        return None
+    if any(t._lazy_cat is None and t.exact_bit() is None for t in tensors):
+        return None
+    lazy = _LazyCat(tensors)
+    if len(lazy.members) > _native.CONCAT_MAX_SOURCES:
+        return None
+    shape = (first.shape[0], sum(t.shape[1] for t in tensors), first.shape[2], first.shape[3])
+    return QTensor(shape, first.device, lazy_cat=lazy, nonneg=all(t.nonneg for t in tensors))
+
+
 def _maxpool(x, kernel_size, stride=None, padding=0, dilation=1, ceil_mode=False, return_indices=False):
     k, s, p = _pair(kernel_size), _pair(stride if stride is not None else kernel_size), _pair(padding)
     if k[0] != k[1] or s[0] != s[1] or p[0] != p[1] or _pair(dilation) != (1, 1) or ceil_mode or return_indices:
@@ -212,12 +276,20 @@ def _maxpool(x, kernel_size, stride=None, padding=0, dilation=1, ceil_mode=False
 def conv_forward(mod, x):
     """NewConv2d.forward in pipeline mode."""
     conv = mod.Conv
-    if isinstance(x, QTensor):
+    cat = isinstance(x, QTensor) and x._lazy_cat is not None
+    if cat:
+        usable = (not mod._explicit_im2col and not getattr(mod, "_smallc", False)
+                  and x.shape[1] <= mod._c_pad and x._lazy_cat.supported(mod.input_bit))
+        if not usable:
+            x = x.dequantize()
+    elif isinstance(x, QTensor):
         usable = (not mod._explicit_im2col and not getattr(mod, "_smallc", False) and x.q8 is not None
                   and x.q8_bit == mod.input_bit and x.q8.shape[-1] == mod._c_pad)
         if not usable:
             x = x.dequantize()
-    if isinstance(x, QTensor):
+    if isinstance(x, QTensor) and cat:
+        q = x._lazy_cat.get(mod.input_bit, mod._c_pad, x.relu_pending and not x.nonneg)   # Concat + Quantity(ib)
+    elif isinstance(x, QTensor):
         q = x.int8_payload()                                     # Quantity(ib) is the identity here
     elif getattr(mod, "_smallc", False):
         _, out8 = mod._smallc_forward(x, want_f32=False, want_s8=True, relu=mod._fuse_relu)

@@ -188,6 +188,65 @@ add_requant_kernel(const AddParams p, size_t n)
     }
 }
 
+
+// Concat + the consumer's input quantiser on quantised operands (pq_concat_requant_s8).  HBM-bound:
+// 1 (int8) or 2 (int16) bytes read + 1 byte written per element.
+struct ConcatParams {
+    const void *ptr[PQ_CONCAT_MAX_SOURCES];
+    int is16[PQ_CONCAT_MAX_SOURCES], channels[PQ_CONCAT_MAX_SOURCES], off[PQ_CONCAT_MAX_SOURCES];
+    int sh[PQ_CONCAT_MAX_SOURCES], relu[PQ_CONCAT_MAX_SOURCES];   // sh = q_bit - bit_i
+    int k, c_out_pad;
+};
+
+// one thread per (pixel, 16 output channels); every channel count is a multiple of 16
+__global__ void __launch_bounds__(kPipeThreads)
+concat_requant_vec_kernel(const ConcatParams p, size_t pixels, int8_t *__restrict__ out)
+{
+    const unsigned int groups = (unsigned int)p.c_out_pad >> 4;
+    const size_t total = pixels * groups;
+    for (size_t t = (size_t)blockIdx.x * kPipeThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kPipeThreads) {
+        const size_t pix = t / groups;
+        const int c0 = (int)(t - pix * groups) << 4;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+        for (int i = 0; i < p.k; ++i) {
+            const int c = c0 - p.off[i];
+            if (c < 0 || c >= p.channels[i]) continue;
+            const size_t v = (pix * (size_t)p.channels[i] + c) >> 4;
+            int x[16];
+            if (p.is16[i]) add_load16<true>(p.ptr[i], v, x); else add_load16<false>(p.ptr[i], v, x);
+            const int lo = p.relu[i] ? 0 : -32768, sh = p.sh[i];
+            int q[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) q[j] = requant_rne(max(x[j], lo), sh);
+            o = make_uint4(pack4_sat_s8(q[0], q[1], q[2], q[3]), pack4_sat_s8(q[4], q[5], q[6], q[7]),
+                           pack4_sat_s8(q[8], q[9], q[10], q[11]), pack4_sat_s8(q[12], q[13], q[14], q[15]));
+            break;
+        }
+        reinterpret_cast<uint4 *>(out)[t] = o;
+    }
+}
+
+// any channel counts: one thread per output element
+__global__ void __launch_bounds__(kPipeThreads)
+concat_requant_scalar_kernel(const ConcatParams p, size_t pixels, int8_t *__restrict__ out)
+{
+    const size_t total = pixels * (size_t)p.c_out_pad;
+    for (size_t t = (size_t)blockIdx.x * kPipeThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kPipeThreads) {
+        const size_t pix = t / (unsigned int)p.c_out_pad;
+        const int c0 = (int)(t - pix * (unsigned int)p.c_out_pad);
+        int q = 0;
+        for (int i = 0; i < p.k; ++i) {
+            const int c = c0 - p.off[i];
+            if (c < 0 || c >= p.channels[i]) continue;
+            int x = add_load(p.ptr[i], p.is16[i], pix * (size_t)p.channels[i] + c);
+            if (p.relu[i]) x = max(x, 0);
+            q = requant_rne(x, p.sh[i]);
+            break;
+        }
+        out[t] = (int8_t)q;
+    }
+}
 }  // namespace pq
 
 namespace {
@@ -262,5 +321,37 @@ extern "C" int pq_add_requant_ex(const void *a, int a_is16, int a_bit, int a_rel
         PQ_ADD_CASE(14, true, true, true, false) PQ_ADD_CASE(15, true, true, true, true)
     }
 #undef PQ_ADD_CASE
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pq_concat_requant_s8(const pq_concat_src *srcs_host, int k, size_t pixels, int q_bit, int c_out_pad,
+                                    int8_t *out, pq_stream_t stream)
+{
+    if (k < 0 || c_out_pad < 0 || (k > 0 && !srcs_host)) return PQ_EINVAL;
+    if (k > PQ_CONCAT_MAX_SOURCES) return PQ_ETOOMANY;
+    if (pixels == 0 || c_out_pad == 0) return PQ_OK;
+    if (!out) return PQ_EINVAL;
+    pq::ConcatParams p;
+    p.k = k; p.c_out_pad = c_out_pad;
+    int off = 0;
+    bool vec = (c_out_pad & 15) == 0 && al16(out);
+    for (int i = 0; i < k; ++i) {
+        const pq_concat_src &s = srcs_host[i];
+        if (s.channels < 0 || (s.channels > 0 && !s.ptr)) return PQ_EINVAL;
+        if (q_bit - s.bit > 15 || s.bit - q_bit > 15) return PQ_EUNSUPPORTED;
+        if (s.is16 && (((unsigned long long)s.ptr) & 1ull)) return PQ_EALIGN;
+        p.ptr[i] = s.ptr; p.is16[i] = s.is16 ? 1 : 0; p.channels[i] = s.channels; p.off[i] = off;
+        p.sh[i] = q_bit - s.bit; p.relu[i] = s.relu ? 1 : 0;
+        vec = vec && (s.channels & 15) == 0 && al16(s.ptr);
+        off += s.channels;
+    }
+    if (off > c_out_pad) return PQ_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec)
+        pq::concat_requant_vec_kernel<<<pipe_grid(pixels * (size_t)(c_out_pad >> 4)), pq::kPipeThreads, 0, st>>>(
+            p, pixels, out);
+    else
+        pq::concat_requant_scalar_kernel<<<pipe_grid(pixels * (size_t)c_out_pad), pq::kPipeThreads, 0, st>>>(
+            p, pixels, out);
     return (int)cudaGetLastError();
 }

@@ -46,6 +46,45 @@ extern "C" int pq_absmax_multi_f32(const float *const *xs_host, const uint64_t *
     return (int)cudaGetLastError();
 }
 
+namespace {
+// m = ceil(2^(31+l) / d), l = ceil(log2 d): floor(n * m / 2^(31+l)) == n / d for every n < 2^31
+void magic31(unsigned int d, unsigned int *m, int *s)
+{
+    int l = 0;
+    while ((1ull << l) < d) ++l;
+    *s = 31 + l;
+    *m = (unsigned int)(((1ull << *s) + d - 1) / d);
+}
+}  // namespace
+
+extern "C" int pq_absmax_per_channel_f32(const float *x, uint64_t outer, int channels, uint64_t inner,
+                                         uint32_t *max_bits, pq_stream_t stream)
+{
+    if (channels < 0) return PQ_EINVAL;
+    if (outer == 0 || channels == 0 || inner == 0) return PQ_OK;
+    if (!x || !max_bits) return PQ_EINVAL;
+    if (((unsigned long long)x & 3ull) != 0) return PQ_EALIGN;
+    if (channels > 8192 || inner >= (1ull << 31) - (1ull << 14) || outer * (uint64_t)channels >= (1ull << 31))
+        return PQ_EUNSUPPORTED;
+    pq::ChannelGeom g;
+    g.total = outer * (uint64_t)channels * inner;
+    g.inner = (unsigned int)inner;
+    g.channels = (unsigned int)channels;
+    magic31(g.inner, &g.m_inner, &g.s_inner);
+    magic31(g.channels, &g.m_chan, &g.s_chan);
+    unsigned long long head = ((16ull - ((unsigned long long)x & 15ull)) & 15ull) >> 2;
+    if (head > g.total) head = g.total;
+    const unsigned long long nvec = (g.total - head) >> 2;
+    const unsigned int tail = (unsigned int)(g.total - head - (nvec << 2));
+    unsigned long long chunks = (nvec + pq::kChunkVecs - 1) / pq::kChunkVecs;
+    if (chunks == 0) chunks = 1;
+    if (chunks > 0xffffffffull) return PQ_EUNSUPPORTED;
+    pq::absmax_per_channel_kernel<<<grid_for((unsigned int)chunks, 8), pq::kStatThreads, (size_t)channels * 4,
+                                    (cudaStream_t)stream>>>(x, g, (unsigned int)head, nvec, tail,
+                                                            (unsigned int)chunks, max_bits);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int pq_hist2048_multi_f32(const float *const *xs_host, const uint64_t *ns_host,
                                      const float *intervals_host, int k, long long *hist,
                                      pq_stream_t stream)

@@ -105,6 +105,122 @@ absmax_multi_kernel(const __grid_constant__ SegTable tab, unsigned int *__restri
     }
 }
 
+// ------------------------------------------------------------------- per-channel absmax
+// Extension of a1 (no reference counterpart): max |x| per channel of a contiguous
+// [outer][channels][inner] tensor.  Same streaming skeleton as absmax_multi_kernel (32 KB chunks,
+// 8 x LDG.128 in flight per thread, 4 algorithmic bytes per element); the extra work is finding the
+// channel of every float4 without dividing.  A CTA owns a contiguous chunk range, so it divides once
+// (64-bit) for its first element and afterwards only needs quotients of numbers below inner + 2^13:
+// those come from a multiply-shift with a host-computed 32-bit magic (exact for numerators < 2^31,
+// Granlund-Montgomery round-up method).  Maxima are kept per CTA in a shared [channels] array;
+// a warp whose 32 float4 lie in one plane (the common case: inner >= 128) folds them with one
+// redux.sync and issues ONE shared atomic.
+struct ChannelGeom {
+    unsigned long long total;       // outer * channels * inner
+    unsigned int inner, channels;
+    unsigned int m_inner, m_chan;   // magics
+    int s_inner, s_chan;            // shifts (31 + ceil(log2 d))
+};
+
+__device__ __forceinline__ unsigned int magic_div(unsigned int n, unsigned int m, int s)
+{
+    return (unsigned int)(((unsigned long long)n * m) >> s);
+}
+
+// slow path: the four elements of a float4 that straddles a plane boundary (or inner < 4)
+__device__ __forceinline__ void chan_add_straddle(unsigned int *smax, const float4 &v, unsigned int rem, unsigned int ch,
+                                                  const ChannelGeom &g)
+{
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        while (rem >= g.inner) {
+            rem -= g.inner;
+            if (++ch == g.channels) ch = 0;
+        }
+        atomicMax(smax + ch, absbits(e[j]));
+        ++rem;
+    }
+}
+
+__global__ void __launch_bounds__(kStatThreads)
+absmax_per_channel_kernel(const float *__restrict__ x, const ChannelGeom g, unsigned int head,
+                          unsigned long long nvec, unsigned int tail, unsigned int total_chunks,
+                          unsigned int *__restrict__ max_bits)
+{
+    extern __shared__ unsigned int s_cmax[];               // [channels]
+    const unsigned int per = (total_chunks + gridDim.x - 1) / gridDim.x;
+    unsigned int c = blockIdx.x * per;
+    const unsigned int c_end = min(c + per, total_chunks);
+    if (c >= c_end) return;
+    for (unsigned int i = threadIdx.x; i < g.channels; i += kStatThreads) s_cmax[i] = 0;
+    __syncthreads();
+
+    const float4 *body = reinterpret_cast<const float4 *>(x + head);
+    // position of this CTA's first body element: plane remainder r0 (< inner) and channel ch0
+    const unsigned long long e0 = (unsigned long long)head + (unsigned long long)c * kChunkElems;
+    const unsigned long long p0 = e0 / g.inner;
+    unsigned int r0 = (unsigned int)(e0 - p0 * g.inner);
+    unsigned int ch0 = (unsigned int)(p0 % g.channels);
+
+    for (; c < c_end; ++c) {
+        const unsigned long long v0 = (unsigned long long)c * kChunkVecs;
+        const float4 *src = body + v0;
+        const unsigned long long left = nvec > v0 ? nvec - v0 : 0;
+        if (left >= (unsigned long long)kChunkVecs) {
+            float4 v[kVecPerThread];
+#pragma unroll
+            for (int i = 0; i < kVecPerThread; ++i) v[i] = ld_stream_f4(src + threadIdx.x + i * kStatThreads);
+#pragma unroll
+            for (int i = 0; i < kVecPerThread; ++i) {
+                const unsigned int r = r0 + 4u * (threadIdx.x + i * kStatThreads);
+                const unsigned int q = magic_div(r, g.m_inner, g.s_inner);
+                const unsigned int rem = r - q * g.inner;
+                unsigned int ch = ch0 + q;
+                ch -= magic_div(ch, g.m_chan, g.s_chan) * g.channels;
+                const unsigned int m4 = max(max(absbits(v[i].x), absbits(v[i].y)), max(absbits(v[i].z), absbits(v[i].w)));
+                const bool whole = rem + 3u < g.inner;     // all four elements in plane `ch`
+                int same;
+                __match_all_sync(0xffffffffu, ch, &same);
+                if (same && __all_sync(0xffffffffu, whole)) {
+                    const unsigned int m = __reduce_max_sync(0xffffffffu, m4);
+                    if ((threadIdx.x & 31) == 0) atomicMax(s_cmax + ch, m);
+                } else if (whole) {
+                    atomicMax(s_cmax + ch, m4);
+                } else {
+                    chan_add_straddle(s_cmax, v[i], rem, ch, g);
+                }
+            }
+        } else {                                           // last, partial chunk: no warp collectives
+            for (unsigned int i = threadIdx.x; i < (unsigned int)left; i += kStatThreads) {
+                const float4 w = ld_stream_f4(src + i);
+                const unsigned int r = r0 + 4u * i;
+                const unsigned int q = magic_div(r, g.m_inner, g.s_inner);
+                unsigned int ch = ch0 + q;
+                ch -= magic_div(ch, g.m_chan, g.s_chan) * g.channels;
+                chan_add_straddle(s_cmax, w, r - q * g.inner, ch, g);
+            }
+        }
+        // advance the CTA's base position by one chunk
+        r0 += kChunkElems;
+        const unsigned int q = magic_div(r0, g.m_inner, g.s_inner);
+        r0 -= q * g.inner;
+        ch0 += q;
+        ch0 -= magic_div(ch0, g.m_chan, g.s_chan) * g.channels;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {             // the unaligned head / tail scalars (<= 3 each)
+        for (unsigned int j = 0; j < head + tail; ++j) {
+            const unsigned long long e = j < head ? j : g.total - tail + (j - head);
+            atomicMax(s_cmax + (unsigned int)((e / g.inner) % g.channels), absbits(x[e]));
+        }
+    }
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < g.channels; i += kStatThreads) {
+        const unsigned int m = s_cmax[i];
+        if (m) atomicMax(max_bits + i, m);
+    }
+}
+
 // --------------------------------------------------------------------------- histogram
 // Bin index of the reference: idx = min((int)trunc(fl32(|x| / interval)), 2047) for x != 0, where
 // the division is IEEE round-to-nearest.  A literal __fdiv_rn costs MUFU.RCP + FCHK + 5 FFMA + a

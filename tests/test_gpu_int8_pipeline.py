@@ -177,3 +177,112 @@ def test_pipeline_fallback_paths_tiny_net(tmp_path):
         model = enable_int8_pipeline(r.ReconModel(r.get_quantity_information(), None).cuda())
         y = model(torch.from_numpy(g["eval_batch"]).cuda())
     assert np.array_equal(y.cpu().numpy(), g["ReconModel/y"])
+
+
+# (channel counts, int16 flags, bits, relu flags, q_bit, c_out_pad)
+CONCAT_CASES = [((32, 64, 16), (False, False, False), (4, 4, 4), (False, False, False), 4, 112),      # pure copy
+                ((32, 64, 16), (False, True, False), (5, 6, 2), (False, True, False), 4, 128),         # vector path
+                ((16, 16), (True, True), (7, 3), (True, True), 0, 32),
+                ((8, 8), (False, False), (3, 5), (False, True), 4, 16),                                # scalar path
+                ((5, 3, 7), (False, True, False), (1, 6, 4), (True, False, False), 7, 32),
+                ((48,), (False,), (2,), (False,), 6, 64)]
+
+
+@pytest.mark.parametrize("case", CONCAT_CASES, ids=["c" + "_".join(map(str, c[0])) + "_q%d" % c[4] for c in CONCAT_CASES])
+def test_concat_requant_vs_oracle(oracle, case):
+    """pq_concat_requant_s8 == Quantity(q_bit)(Concat(de-quantised members)) (the reference composition)."""
+    from common.quantity import _native
+    chans, is16, bits, relus, q_bit, c_pad = case
+    rng = np.random.default_rng(sum(chans) + q_bit)
+    N, H, W = 3, 7, 9
+    srcs, parts = [], []
+    for c, w16, bit, relu in zip(chans, is16, bits, relus):
+        lo, hi = (-128 * 2 ** bit, 127 * 2 ** bit) if w16 else (-128, 127)
+        v = rng.integers(lo, hi + 1, size=(N, H, W, c)).astype(np.int16 if w16 else np.int8)
+        v.reshape(-1)[:4] = [lo, hi, 0, -1]
+        srcs.append((torch.from_numpy(v).cuda(), bit, relu))
+        real = v.astype(np.float32) / np.float32(2.0 ** bit)
+        parts.append(np.maximum(real, 0) if relu else real)
+    want = oracle.concat_quantize([p.transpose(0, 3, 1, 2) for p in parts], q_bit)      # fp32 NCHW
+    got = _native.concat_requant_s8(srcs, q_bit, c_pad).cpu().numpy()
+    assert got.shape == (N, H, W, c_pad)
+    assert np.array_equal(got[..., :sum(chans)].transpose(0, 3, 1, 2).astype(np.float32), want)
+    assert not got[..., sum(chans):].any()                                             # channel padding is zero
+
+
+def test_concat_requant_errors():
+    from common.quantity import _native
+    a = torch.zeros((1, 2, 2, 16), dtype=torch.int8, device="cuda")
+    with pytest.raises(RuntimeError):
+        _native.concat_requant_s8([(a, 4, False)], 4, 8)             # output narrower than the sources
+    with pytest.raises(RuntimeError):
+        _native.concat_requant_s8([(a, 20, False)], 0, 16)           # shift out of range
+    with pytest.raises(RuntimeError):
+        _native.concat_requant_s8([(a, 4, False)] * 9, 4, 256)       # too many sources
+
+
+class _WideCatNet(torch.nn.Module):
+    """Concat of 32- and 64-channel branches (vector path of the concat kernel), a nested concat, a ReLU
+    between Concat and its consumer, and an Eltwise whose int16 sum feeds a Concat."""
+
+    def __init__(self):
+        super().__init__()
+        from common.quantity import Concat, Eltwise, View
+        nn = torch.nn
+        self.stem = nn.Sequential(nn.Conv2d(3, 32, 3, padding=1, bias=False), nn.BatchNorm2d(32), nn.ReLU(False))
+        self.a = nn.Sequential(nn.Conv2d(32, 32, 3, padding=1, bias=False), nn.BatchNorm2d(32))
+        self.b = nn.Sequential(nn.Conv2d(32, 64, 1, bias=True), nn.BatchNorm2d(64), nn.ReLU(False))
+        self.cat1 = Concat()
+        self.relu1 = nn.ReLU(False)
+        self.c = nn.Sequential(nn.Conv2d(96, 32, 3, padding=1, bias=False), nn.BatchNorm2d(32))
+        self.add = Eltwise()
+        self.cat2 = Concat()
+        self.cat3 = Concat()
+        self.d = nn.Sequential(nn.Conv2d(32 + 32 + 96, 48, 1, bias=False), nn.BatchNorm2d(48), nn.ReLU(False))
+        self.pool = nn.AvgPool2d(12)
+        self.view = View()
+        self.fc = nn.Linear(48, 10)
+
+    def forward(self, x):
+        s = self.stem(x)
+        cat1 = self.relu1(self.cat1(self.a(s), self.b(s)))
+        e = self.add(self.c(cat1), s)
+        cat3 = self.cat3(self.cat2(e, s), cat1)                     # nested: (Eltwise sum, stem) ++ cat1
+        return self.fc(self.view(self.pool(self.d(cat3))))
+
+
+def test_pipeline_concat_stays_quantised(tmp_path):
+    import tools
+    from common.quantity import _native, enable_int8_pipeline, merge_bn
+    from test_gpu_e2e import _configs
+
+    def build():
+        torch.manual_seed(3)
+        net = _WideCatNet().eval()
+        g = torch.Generator().manual_seed(11)
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+                m.weight.data.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        return net
+
+    cfg, user = _configs(tmp_path, (1, 3, 12, 12), 2)
+    with torch.no_grad():
+        q = tools.Quantity(merge_bn(build(), "cpu"), config=cfg, user_config=user, verbose=False)
+        q.activation_quantize([(torch.randn(4, 3, 12, 12, generator=torch.Generator().manual_seed(1 + i)), None)
+                               for i in range(3)])
+        q.weight_quantize()
+        r = tools.Reconstruction(build(), config=cfg)
+        r.merge_bn()
+        model = r.ReconModel(r.get_quantity_information(), None).cuda().eval()
+        x = torch.randn(5, 3, 12, 12, generator=torch.Generator().manual_seed(42)).cuda()
+        ref = model(x)
+        enable_int8_pipeline(model)
+        before = _native.LAUNCHES.get("concat_requant", 0)
+        out = model(x)
+        assert _native.LAUNCHES.get("concat_requant", 0) - before == 2, "Concat consumers did not use the int8 kernel"
+        assert torch.equal(out, ref)
+        enable_int8_pipeline(model, False)
+        assert torch.equal(model(x), ref)

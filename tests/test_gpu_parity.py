@@ -282,3 +282,55 @@ def test_abi_error_codes(cq):
     assert lib.pq_hist2048_multi_f32(ptrs, ns, iv, 1, h.data_ptr(), None) == -1                  # interval <= 0
     with pytest.raises(RuntimeError):
         cq.QuanDequan(8, 3)(torch.zeros(4))                                                       # CPU tensor: no fallback
+
+
+# ---------------------------------------------------------------- per-channel max-abs (extension of a1)
+CHANNEL_CASES = [((4, 64, 56, 56), 1), ((2, 1000), 1), ((3, 7, 5, 3), 1), ((1, 2048, 7, 7), 1), ((5, 3, 224, 224), 1),
+                 ((2, 16, 1, 1), 1), ((64, 3, 7, 7), 0), ((512, 2048), 0), ((6, 13, 3), 1), ((1, 1, 1), 1),
+                 ((3, 8192, 2, 2), 1), ((32, 256, 56, 56), 1)]
+
+
+@pytest.mark.parametrize("shape,dim", CHANNEL_CASES, ids=["x".join(map(str, s)) + "_d%d" % d for s, d in CHANNEL_CASES])
+def test_absmax_per_channel_vs_oracle(cq, oracle, shape, dim):
+    from common.quantity import _native
+    g = torch.Generator(device="cuda").manual_seed(len(shape) * 1000 + shape[-1])
+    x = torch.randn(shape, device="cuda", generator=g)
+    x.view(-1)[::max(1, x.numel() // 97)] *= 7.0                       # isolated peaks in various planes
+    bits = torch.zeros(shape[dim], dtype=torch.int32, device="cuda")
+    _native.absmax_per_channel(x, bits, dim)
+    want = oracle.absmax_per_channel(x.cpu().numpy(), dim)
+    assert np.array_equal(bits.view(torch.float32).cpu().numpy(), want)
+    # a second batch accumulates into the running maxima; per-tensor max == max over channels
+    x2 = torch.randn(shape, device="cuda", generator=g) * 1.5
+    _native.absmax_per_channel(x2, bits, dim)
+    want2 = oracle.absmax_per_channel(x2.cpu().numpy(), dim, cur=want)
+    assert np.array_equal(bits.view(torch.float32).cpu().numpy(), want2)
+    assert float(want2.max()) == float(max(x.abs().max(), x2.abs().max()))
+
+
+@pytest.mark.parametrize("offset", [1, 2, 3])
+def test_absmax_per_channel_unaligned_view(cq, oracle, offset):
+    from common.quantity import _native
+    base = torch.randn(4 * 24 * 11 * 13 + 8, device="cuda", generator=torch.Generator(device="cuda").manual_seed(offset))
+    x = base[offset:offset + 4 * 24 * 11 * 13].view(4, 24, 11, 13)      # 4-byte aligned only
+    bits = torch.zeros(24, dtype=torch.int32, device="cuda")
+    _native.absmax_per_channel(x, bits, 1)
+    assert np.array_equal(bits.view(torch.float32).cpu().numpy(), oracle.absmax_per_channel(x.cpu().numpy(), 1))
+
+
+def test_collector_channel_max_extension(cq, oracle):
+    names = ["a", "b"]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    batches = [{"a": torch.randn(2, 16, 9, 9, device="cuda", generator=g),
+                "b": torch.randn(2, 10, device="cuda", generator=g)} for _ in range(3)]
+    dc = cq.DistributionCollector(names)
+    for b in batches:
+        dc.refresh_max_val({k: v.view(-1) for k, v in b.items()})
+        dc.refresh_channel_max_val(b)
+    got = dc.channel_max_vals
+    for n in names:
+        want = None
+        for b in batches:
+            want = oracle.absmax_per_channel(b[n].cpu().numpy(), 1, cur=want)
+        assert np.array_equal(got[n], want)
+        assert np.float32(got[n].max()) == dc.max_vals[n]             # consistent with the per-tensor reduction

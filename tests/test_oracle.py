@@ -217,3 +217,66 @@ def test_tiny_recon_outputs(oracle):
     out = torch.nn.functional.conv2d(torch.from_numpy(x), torch.from_numpy(wq), torch.from_numpy(bq), 1, 1)
     assert np.array_equal(oracle.fakequant(out.numpy(), info["conv0.0"]["output_bit"]),
                           g["ReconTest/layer/conv0.0"])
+
+
+def _requant_int(v, sh, relu):
+    """The integer formula pq_concat_requant_s8 / pq_add_requant implement: round_half_even(v * 2^sh), saturated."""
+    v = np.maximum(v.astype(np.int64), 0) if relu else v.astype(np.int64)
+    if sh >= 0:
+        r = np.clip(v, -128, 127) << sh
+    else:
+        d = -sh
+        r = (v + (1 << (d - 1)) - 1 + ((v >> d) & 1)) >> d
+    return np.clip(r, -128, 127)
+
+
+def test_tiny_concat_composition(oracle):
+    """Concat -> ReLU -> NewConv2d of the reference (golden layer outputs) from the oracle's restatements, and
+    the integer requantisation formula of the concat kernel against that composition."""
+    import tiny_fabu_net as tn
+    g = load_golden("tiny_e2e.npz")
+    info = golden_json(g)["quantity_information"]
+    a, b = g["ReconModel/layer/branch_a.0"], g["ReconModel/layer/branch_b.0"]
+    cat = np.maximum(np.concatenate([a, b], axis=1), 0)                    # Concat, relu1
+    net = tn.build_tiny(0)
+    sd = {k[len("state/"):]: g[k] for k in g.files if k.startswith("state/")}
+    conv, bn = "conv_c.0", "conv_c.1"
+    w, bias = oracle.merge_bn_params(sd[conv + ".weight"], None, sd[bn + ".weight"], sd[bn + ".bias"],
+                                     sd[bn + ".running_mean"], sd[bn + ".running_var"])
+    y, _ = oracle.int_conv_layer(cat, w, bias, info[conv], stride=1, padding=1)
+    assert np.array_equal(y, g["ReconModel/layer/conv_c.0"])
+    # integer payloads of the two branches at their own output bits -> the consumer's int8 operand
+    ib = info[conv]["input_bit"]
+    want = oracle.concat_quantize([np.maximum(a, 0), np.maximum(b, 0)], ib)
+    parts = []
+    for name, v in (("branch_a.0", a), ("branch_b.0", b)):
+        ob = info[name]["output_bit"]
+        payload = v * np.float32(2.0 ** ob)
+        assert np.array_equal(payload, np.rint(payload)) and np.abs(payload).max() <= 128
+        parts.append(_requant_int(payload.astype(np.int64), ib - ob, relu=True))
+    assert np.array_equal(np.concatenate(parts, axis=1).astype(np.float32), want)
+
+
+def test_requant_formula_matches_quantity_composition(oracle):
+    """Every (payload bit, consumer bit) pair: the integer formula equals Quantity(q)(payload / 2^bit)."""
+    v8 = np.arange(-128, 128, dtype=np.int64)
+    for bit in range(0, 8):
+        v16 = np.arange(-128 * 2 ** bit, 127 * 2 ** bit + 1, dtype=np.int64)
+        for q in range(-4, 12):
+            for v in (v8, v16):
+                for relu in (False, True):
+                    real = v.astype(np.float32) / np.float32(2.0 ** bit)
+                    real = np.maximum(real, 0) if relu else real
+                    assert np.array_equal(_requant_int(v, q - bit, relu), oracle.quantize_input(real, q)), (bit, q, relu)
+
+
+def test_absmax_per_channel_oracle_consistency(oracle):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((3, 5, 4, 6)).astype(np.float32)
+    pc = oracle.absmax_per_channel(x, 1)
+    assert pc.shape == (5,) and pc.dtype == np.float32
+    for c in range(5):
+        assert pc[c] == oracle.absmax_update(0, x[:, c])                    # the reference's per-tensor rule per plane
+    assert pc.max() == oracle.absmax_update(0, x)
+    w = rng.standard_normal((7, 3, 3, 3)).astype(np.float32)
+    assert np.array_equal(oracle.absmax_per_channel(w, 0), np.abs(w).reshape(7, -1).max(axis=1))
