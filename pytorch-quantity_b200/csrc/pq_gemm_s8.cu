@@ -58,6 +58,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+// One leader lane per warp (deterministic for a given member mask).  The producer and MMA loops are
+// executed by the WHOLE warp with only the asynchronous instructions predicated on the leader, so that
+// tile / stage / coordinate arithmetic stays warp-uniform (uniform datapath, no R2UR waterfall loops):
+// a single-lane loop needed ~100 dependent instructions per K block and bounded the short-K layers.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -73,11 +88,47 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// variants taking precomputed shared-window addresses
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_a(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                              int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_a(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c, int w,
+                                                     int h, int n, uint16_t off_w, uint16_t off_h)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_a(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2,
@@ -156,6 +207,10 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], int8 operands, int32 accumulate
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -551,7 +606,7 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool fast_epi = p.stage_s8 && !p.out_f32;                    // which epilogue configuration runs
     const int kAcc = fast_epi ? EpiCfg<BN, true>::kAcc : EpiCfg<BN, false>::kAcc;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
     constexpr uint32_t kTmemCols = EpiCfg<BN, true>::kTmemCols;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int total_tiles = (p.a_im2col == 2 ? p.M / kBM : (p.M + kBM - 1) / kBM) * n_tiles;   // mode 2: M = patches * 128
@@ -569,75 +624,83 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            const int pq = p.P * p.Q;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
-                int wq = 0, hp = 0, nb = 0;
-                if (p.a_im2col == 1) {                 // first output pixel of the tile -> input coords
-                    nb = m0 / pq;
-                    const int rem = m0 - nb * pq;
-                    hp = rem / p.Q;
-                    wq = rem - hp * p.Q;
+        // ===================== TMA producer (whole warp, leader lane issues) =====================
+        const bool leader = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        const int pq = p.P * p.Q;
+        const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b), full_base = smem_u32(full_bar);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
+            int wq = 0, hp = 0, nb = 0;
+            if (p.a_im2col == 1) {                 // first output pixel of the tile -> input coords
+                nb = m0 / pq;
+                const int rem = m0 - nb * pq;
+                hp = rem / p.Q;
+                wq = rem - hp * p.Q;
+            }
+            if (p.a_im2col == 2) {                 // patch -> (image, first output row, first output column)
+                const int mt = tile / n_tiles, per_img = p.tiles_p * p.tiles_q;
+                nb = mt / per_img;
+                const int rem = mt - nb * per_img;
+                hp = (rem / p.tiles_q) * p.TH;
+                wq = (rem % p.tiles_q) * p.TW;
+            }
+            const int w0 = wq * p.stride_w - p.pad_w, h0 = hp * p.stride_h - p.pad_h;
+            int r = 0, s = 0, cb = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(empty_bar + stage, phase ^ 1);
+                if (leader) {
+                    const uint32_t bar = full_base + (uint32_t)stage * 8u;
+                    const uint32_t dst_a = a_base + (uint32_t)stage * (uint32_t)Cfg::kABytes;
+                    const uint32_t dst_b = b_base + (uint32_t)stage * (uint32_t)Cfg::kBBytes;
+                    mbar_expect_tx_a(bar, Cfg::kStageBytes);
+                    if (p.a_im2col == 2)               // filter row kb: padded input row = p * stride_h + kb
+                        tma_load_5d_a(&tmap_a, bar, dst_a, 0, wq, hp + kb / p.stride_h, kb % p.stride_h, nb);
+                    else if (p.a_im2col)
+                        tma_load_im2col_4d_a(&tmap_a, bar, dst_a, cb * BK, w0, h0, nb, (uint16_t)s, (uint16_t)r);
+                    else
+                        tma_load_2d_a(&tmap_a, bar, dst_a, kb * BK, m0);
+                    // weights [N][R*S*C]: the K offset of tap (r, s), channel block cb is kb * BK (C == cblocks * BK)
+                    tma_load_2d_a(&tmap_b, bar, dst_b, kb * BK, n0);
                 }
-                if (p.a_im2col == 2) {                 // patch -> (image, first output row, first output column)
-                    const int mt = tile / n_tiles, per_img = p.tiles_p * p.tiles_q;
-                    nb = mt / per_img;
-                    const int rem = mt - nb * per_img;
-                    hp = (rem / p.tiles_q) * p.TH;
-                    wq = (rem % p.tiles_q) * p.TW;
-                }
-                int r = 0, s = 0, cb = 0;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(empty_bar + stage, phase ^ 1);
-                    mbar_expect_tx(full_bar + stage, Cfg::kStageBytes);
-                    void *dst_a = smem_a + (size_t)stage * Cfg::kABytes;
-                    void *dst_b = smem_b + (size_t)stage * Cfg::kBBytes;
-                    if (p.a_im2col == 2) {             // filter row kb: padded input row = p * stride_h + kb
-                        tma_load_5d(&tmap_a, full_bar + stage, dst_a, 0, wq, hp + kb / p.stride_h, kb % p.stride_h, nb);
-                        tma_load_2d(&tmap_b, full_bar + stage, dst_b, kb * BK, n0);
-                    } else if (p.a_im2col) {
-                        tma_load_im2col_4d(&tmap_a, full_bar + stage, dst_a, cb * BK, wq * p.stride_w - p.pad_w,
-                                           hp * p.stride_h - p.pad_h, nb, (uint16_t)s, (uint16_t)r);
-                        tma_load_2d(&tmap_b, full_bar + stage, dst_b, (r * p.S + s) * p.C + cb * BK, n0);
-                        if (++cb == p.cblocks) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
-                    } else {
-                        tma_load_2d(&tmap_a, full_bar + stage, dst_a, kb * BK, m0);
-                        tma_load_2d(&tmap_b, full_bar + stage, dst_b, kb * BK, n0);
-                    }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
+                __syncwarp();
+                if (++cb == p.cblocks) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_i8(kBM, BN < 16 ? 16 : BN);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);      // epilogue has drained this accumulator
+        // ===================== MMA issuer (whole warp, leader lane issues) =====================
+        constexpr uint32_t idesc = make_idesc_i8(kBM, BN < 16 ? 16 : BN);
+        const bool leader = elect_one();
+        const uint64_t da0 = make_smem_desc<BK>(smem_u32(smem_a)), db0 = make_smem_desc<BK>(smem_u32(smem_b));
+        const uint32_t empty_base = smem_u32(empty_bar), tfull_base = smem_u32(tmem_full_bar);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);      // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(full_bar + stage, phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(full_bar + stage, phase);
-                    tc_fence_after();
-                    const uint64_t da = make_smem_desc<BK>(smem_u32(smem_a + (size_t)stage * Cfg::kABytes));
-                    const uint64_t db = make_smem_desc<BK>(smem_u32(smem_b + (size_t)stage * Cfg::kBBytes));
+                if (leader) {
+                    // the 14-bit start-address field advances by bytes / 16 (shared addresses stay below 2^18)
+                    const uint64_t da = da0 + (uint64_t)(uint32_t)(stage * (Cfg::kABytes >> 4));
+                    const uint64_t db = db0 + (uint64_t)(uint32_t)(stage * (Cfg::kBBytes >> 4));
 #pragma unroll
                     for (int k = 0; k < BK / 32; ++k)  // UMMA_K = 32 int8: advance 32 B inside the swizzle span
                         umma_i8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    umma_commit(empty_bar + stage);    // frees the smem slot when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit_a(empty_base + (uint32_t)stage * 8u);    // frees the smem slot when these MMAs retire
                 }
-                umma_commit(tmem_full_bar + acc);      // accumulator complete
-                if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (leader) umma_commit_a(tfull_base + (uint32_t)acc * 8u);  // accumulator complete
+            __syncwarp();
+            if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ===================== epilogue (warps 2..17) =====================
@@ -704,7 +767,7 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
     const int kAcc = fast_epi ? EpiCfg<BN, true>::kAcc : EpiCfg<BN, false>::kAcc;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_bar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
     constexpr uint32_t kTmemCols = EpiCfg<BN, true>::kTmemCols;
     const int total_tiles = (p.M / kBM) * n_tiles;
     const int per_img = p.tiles_p * p.tiles_q;
@@ -722,54 +785,74 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
+    // Both loops below run on the whole warp with the asynchronous instructions predicated on one leader
+    // lane, and walk the tiles incrementally (no per-tile division): the single-lane version spent ~390
+    // dependent instructions per tile in the MMA warp and starved the epilogue (ncu: 60 % of all stall
+    // samples were epilogue warps waiting for an accumulator).
     if (warp == 0) {
-        if (lane == 0) {
-            // weights: resident for the whole kernel
+        const bool leader = elect_one();
+        if (leader) {                                  // weights: resident for the whole kernel
             mbar_expect_tx(b_bar, (uint32_t)(n_tiles * p.R * BN * BK));
             for (int nt = 0; nt < n_tiles; ++nt)
                 for (int r = 0; r < p.R; ++r)
                     tma_load_2d(&tmap_b, b_bar, smem_b + (size_t)(nt * p.R + r) * (BN * BK), r * BK, nt * BN);
-            int stage = 0; uint32_t phase = 0;
-            const uint32_t bytes = (uint32_t)(p.R * rp.pitch);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / n_tiles;
-                const int img = mt / per_img, prow = (mt - img * per_img) / p.tiles_q;
-                mbar_wait(empty_bar + stage, phase ^ 1);
-                mbar_expect_tx(full_bar + stage, bytes);
-                bulk_load_1d(smem_a + (size_t)stage * rp.a_stage,
-                             rp.xp + ((size_t)img * rp.Hp + (size_t)prow * p.stride_h) * rp.pitch, bytes, full_bar + stage);
-                if (++stage == rp.stages) { stage = 0; phase ^= 1; }
+        }
+        __syncwarp();
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t bytes = (uint32_t)(p.R * rp.pitch);
+        const uint32_t a_base = smem_u32(smem_a), full_base = smem_u32(full_bar);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = n_tiles == 1 ? tile : tile / n_tiles;
+            const int img = mt / per_img, prow = (mt - img * per_img) / p.tiles_q;
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            if (leader) {
+                const uint32_t bar = full_base + (uint32_t)stage * 8u;
+                mbar_expect_tx_a(bar, bytes);
+                bulk_load_1d_a(a_base + (uint32_t)(stage * rp.a_stage),
+                               rp.xp + ((size_t)img * rp.Hp + (size_t)prow * p.stride_h) * rp.pitch, bytes, bar);
             }
+            __syncwarp();
+            if (++stage == rp.stages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_i8(kBM, BN);
-            mbar_wait(b_bar, 0);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-                const int q0 = ((mt % per_img) % p.tiles_q) * kBM;
-                mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
-                mbar_wait(full_bar + stage, phase);
-                tc_fence_after();
+        constexpr uint32_t idesc = make_idesc_i8(kBM, BN);
+        const bool leader = elect_one();
+        mbar_wait(b_bar, 0);
+        const uint64_t da0 = make_smem_desc_interleave(smem_u32(smem_a));
+        const uint64_t db0 = make_smem_desc<BK>(smem_u32(smem_b));
+        const uint32_t a_step = (uint32_t)(rp.pitch >> 4);           // one filter row down (pitch % 16 == 0)
+        const uint32_t empty_base = smem_u32(empty_bar), tfull_base = smem_u32(tmem_full_bar);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int nt = 0, q0 = 0;
+            if (n_tiles != 1 || p.tiles_q != 1) {                    // (the ResNet stem has one tile per output row)
+                const int mt = tile / n_tiles;
+                nt = tile - mt * n_tiles;
+                q0 = ((mt % per_img) % p.tiles_q) * kBM;
+            }
+            mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
+            mbar_wait(full_bar + stage, phase);
+            tc_fence_after();
+            if (leader) {
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                const uint32_t a0 = smem_u32(smem_a + (size_t)stage * rp.a_stage) + (uint32_t)(q0 * 16);
-                const uint32_t b0 = smem_u32(smem_b + (size_t)nt * p.R * (BN * BK));
+                uint64_t da = da0 + (uint64_t)(uint32_t)((stage * rp.a_stage + q0 * 16) >> 4);
+                uint64_t db = db0 + (uint64_t)(uint32_t)((nt * p.R * (BN * BK)) >> 4);
                 for (int r = 0; r < p.R; ++r) {
-                    const uint64_t db = make_smem_desc<BK>(b0 + (uint32_t)(r * BN * BK));
 #pragma unroll
                     for (int k = 0; k < BK / 32; ++k)
-                        umma_i8(tmem_d, make_smem_desc_interleave(a0 + (uint32_t)(r * rp.pitch + k * 32)),
-                                db + (uint64_t)(2 * k), idesc, (r | k) != 0);
+                        umma_i8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (r | k) != 0);
+                    da += a_step;
+                    db += (BN * BK) >> 4;
                 }
-                umma_commit(empty_bar + stage);
-                umma_commit(tmem_full_bar + acc);
-                if (++stage == rp.stages) { stage = 0; phase ^= 1; }
-                if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
+                umma_commit_a(empty_base + (uint32_t)stage * 8u);
+                umma_commit_a(tfull_base + (uint32_t)acc * 8u);
             }
+            __syncwarp();
+            if (++stage == rp.stages) { stage = 0; phase ^= 1; }
+            if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         const bool fast = fast_epi;

@@ -11,7 +11,7 @@ tail -3 gpurun_out/bench_stats.err | cut -c1-300; cat gpurun_out/bench_stats.jso
 timeout 900 python bench.py --steps 8 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 tail -3 gpurun_out/bench.err | cut -c1-300; cat gpurun_out/bench.json
 # ncu: per-channel max-abs, histogram on the single-bin worst case, fake-quant, add_requant, stem row kernel
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:absmax_per_channel -s 2 -c 1 \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:absmax_per_channel -s 0 -c 1 \
     -f -o gpurun_out/prof_absmax_per_channel python -m pytest tests/test_gpu_parity.py -q -m gpu -k "per_channel_vs_oracle and 32x256" > gpurun_out/ncu_chan.log 2>&1
 echo "chan rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:hist_multi -s 3 -c 1 \

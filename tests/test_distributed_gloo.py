@@ -54,6 +54,14 @@ def _worker(rank, world, port, out_dir):
     np.save(os.path.join(out_dir, "merged_max%d.npy" % rank), np.array([float(mv[n]) for n in names]))
     np.save(os.path.join(out_dir, "merged_hist%d.npy" % rank), col._hist.numpy())
     assert col.distributions["a"].dtype == np.int64      # counts above 2^31 are not narrowed
+    # --- per-channel maxima (extension): one MAX all-reduce per tensor on the bit patterns
+    chan = rng.random((2, 5)).astype(np.float32)
+    col._chan_bits = {"a": torch.from_numpy(chan[0].view(np.int32).copy()),
+                      "c": torch.from_numpy(chan[1].view(np.int32).copy())}
+    np.save(os.path.join(out_dir, "chan%d.npy" % rank), chan)
+    col.all_reduce_channel_max()
+    np.save(os.path.join(out_dir, "merged_chan%d.npy" % rank),
+            np.stack([col.channel_max_vals["a"], col.channel_max_vals["c"]]))
     dist.destroy_process_group()
 
 
@@ -69,3 +77,6 @@ def test_two_rank_sharding_and_merge(tmp_path):
         assert np.array_equal(np.load(tmp_path / ("merged_max%d.npy" % r)),
                               maxima.max(axis=0).astype(np.float64))        # integer MAX on bit patterns == float max
         assert np.array_equal(np.load(tmp_path / ("merged_hist%d.npy" % r)), hists.sum(axis=0))
+    chans = np.stack([np.load(tmp_path / ("chan%d.npy" % r)) for r in range(world)])
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / ("merged_chan%d.npy" % r)), chans.max(axis=0))
