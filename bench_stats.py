@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench_stats.py -- statistics microbenchmark (BASELINE.json config 5, SURVEY.md 8d "C5").
 
-    python bench_stats.py [--max-log2 32] [--min-log2 28] [--iters 5] [--skip-fakequant]
+    python bench_stats.py [--max-log2 32] [--min-log2 28] [--iters 5] [--skip-stats] [--skip-channel] [--skip-fakequant]
 
 Part 1: max-abs + 2048-bin histogram + KL search over ONE fp32 tensor of 2^28 ... 2^32 elements
         (1 - 16 GB) for the four input families SURVEY 8d names:
@@ -11,6 +11,7 @@ Part 1: max-abs + 2048-bin histogram + KL search over ONE fp32 tensor of 2^28 ..
           outlier   Laplace + one 1e4 outlier        (everything lands in bins 0-3)
         Both statistics kernels are HBM-bound at 4 algorithmic bytes per element; the KL search
         reads 16 KB per tensor and is reported in microseconds.
+Part 1b: per-channel max-abs (extension kernel) over activation-, FC- and weight-shaped tensors.
 Part 2: fake-quant bandwidth sweep, 2^20 ... 2^32 elements x bit in {-2, 0, 4, 7, 12},
         8 algorithmic bytes per element.  Sizes whose working set would fit in the 126 MB L2 rotate
         over enough buffers to exceed 2x L2, so every number is an HBM number.
@@ -105,6 +106,21 @@ def stats_case(kind, log2n, iters, peak):
             "nonzero_fraction": round(nonzero / n, 4), "counts_check": "sum(counts) == count_nonzero(x)"}
 
 
+def channel_case(shape, dim, iters, peak):
+    """Per-channel max-abs (extension of a1): 4 algorithmic bytes per element; checked against torch.amax."""
+    from common.quantity import _native
+    n = int(np.prod(shape))
+    x = make_input("dense", n, 4321).view(shape)
+    bits = torch.zeros(shape[dim], dtype=torch.int32, device="cuda")
+    ms = timed(lambda: _native.absmax_per_channel(x, bits, dim), iters)
+    want = x.abs().amax(dim=[d for d in range(len(shape)) if d != dim])
+    assert torch.equal(bits.view(torch.float32), want), "per-channel max-abs differs from torch.amax"
+    gbs = 4.0 * n / (ms * 1e-3) / 1e9
+    del x
+    return {"bench": "absmax_per_channel", "shape": list(shape), "channel_dim": dim, "GB": round(4.0 * n / 2 ** 30, 3),
+            "ms": round(ms, 4), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
+
+
 def fakequant_case(log2n, bit, iters, peak):
     from common.quantity import _native
     n = 1 << log2n
@@ -139,6 +155,7 @@ def main():
     ap.add_argument("--families", default=",".join(FAMILIES))
     ap.add_argument("--skip-stats", action="store_true")
     ap.add_argument("--skip-fakequant", action="store_true")
+    ap.add_argument("--skip-channel", action="store_true")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench_stats.py needs a CUDA device (no CPU fallback)")
@@ -152,6 +169,11 @@ def main():
             for kind in args.families.split(","):
                 print(json.dumps(stats_case(kind, log2n, args.iters, peak)), flush=True)
                 torch.cuda.empty_cache()
+    if not args.skip_channel:
+        for shape, dim in (((64, 256, 128, 128), 1), ((256, 64, 112, 112), 1), ((512, 512, 28, 28), 1),
+                           ((2674, 2048, 7, 7), 1), ((65536, 1000), 1), ((2048, 512, 3, 3), 0)):
+            print(json.dumps(channel_case(shape, dim, args.iters, peak)), flush=True)
+            torch.cuda.empty_cache()
     if not args.skip_fakequant:
         for log2n in range(20, args.max_log2 + 1, 2):
             for bit in (-2, 0, 4, 7, 12):

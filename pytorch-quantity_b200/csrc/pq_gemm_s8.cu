@@ -27,7 +27,8 @@ namespace pq {
 
 constexpr int kBM = 128;               // UMMA M (cta_group::1): one TMEM lane per output row
 constexpr int kEpiWarps = 16;           // four per TMEM lane quadrant
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // TMA warp, MMA warp, epilogue warps
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps + 32;   // A-operand TMA warp, MMA warp, epilogue warps, B-operand TMA warp
+constexpr int kWarpB = 2 + kEpiWarps;   // the B-operand producer is the last warp (the epilogue keeps warps 2..17)
 
 // ------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -587,8 +588,58 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
     if (staged && lane == 0) bulk_wait_read0();
 }
 
+// A-operand producer loop, specialised per addressing mode (0: 2-D [M][K] tiles, 1: im2col over NHWC,
+// 2: overlapping-stride 5-D windows for <= 8 input channels).  Runs on a whole warp; only the leader
+// lane issues.  Arrives on full_bar with the A bytes of the stage (the B producer adds its own).
+template <int MODE, int BK, int STAGES>
+__device__ __forceinline__ void produce_a(const GemmParams &p, const CUtensorMap *tmap_a, uint8_t *smem_a,
+                                          uint64_t *full_bar, uint64_t *empty_bar, int total_tiles, int n_tiles)
+{
+    constexpr uint32_t kABytes = kBM * BK;
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    const int pq = p.P * p.Q;
+    const uint32_t a_base = smem_u32(smem_a), full_base = smem_u32(full_bar);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = n_tiles == 1 ? tile : tile / n_tiles;
+        const int m0 = mt * kBM;
+        int wq = 0, hp = 0, nb = 0;
+        if (MODE == 1) {                       // first output pixel of the tile -> input coords
+            nb = m0 / pq;
+            const int rem = m0 - nb * pq;
+            hp = rem / p.Q;
+            wq = rem - hp * p.Q;
+        }
+        if (MODE == 2) {                       // patch -> (image, first output row, first output column)
+            const int per_img = p.tiles_p * p.tiles_q;
+            nb = mt / per_img;
+            const int rem = mt - nb * per_img;
+            hp = (rem / p.tiles_q) * p.TH;
+            wq = (rem % p.tiles_q) * p.TW;
+        }
+        const int w0 = wq * p.stride_w - p.pad_w, h0 = hp * p.stride_h - p.pad_h;
+        int r = 0, s = 0, cb = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            if (leader) {
+                const uint32_t bar = full_base + (uint32_t)stage * 8u;
+                const uint32_t dst = a_base + (uint32_t)stage * kABytes;
+                mbar_expect_tx_a(bar, kABytes);
+                if (MODE == 2)                 // filter row kb: padded input row = p * stride_h + kb
+                    tma_load_5d_a(tmap_a, bar, dst, 0, wq, hp + kb / p.stride_h, kb % p.stride_h, nb);
+                else if (MODE == 1)
+                    tma_load_im2col_4d_a(tmap_a, bar, dst, cb * BK, w0, h0, nb, (uint16_t)s, (uint16_t)r);
+                else
+                    tma_load_2d_a(tmap_a, bar, dst, kb * BK, m0);
+            }
+            if (MODE == 1) { if (++cb == p.cblocks) { cb = 0; if (++s == p.S) { s = 0; ++r; } } }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+}
+
 template <int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 1)     // 18 warps = 5 on one SM sub-partition: 96 registers / thread
+__global__ void __launch_bounds__(kGemmThreads, 1)     // 19 warps = 5 on one SM sub-partition: <= 104 registers / thread
 gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const GemmParams p)
 {
@@ -615,7 +666,7 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         if (p.stage_s8) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 2); mbar_init(empty_bar + s, 1); }   // A and B producers
         const int arrivals = fast_epi ? EpiCfg<BN, true>::kWarpsPerAcc : EpiCfg<BN, false>::kWarpsPerAcc;
         for (int s = 0; s < kAcc; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, arrivals); }
         fence_barrier_init();
@@ -627,47 +678,28 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
-        // ===================== TMA producer (whole warp, leader lane issues) =====================
+        // ===================== A-operand TMA producer (whole warp, leader lane issues) =====================
+        // One warp per operand: a single warp's dependent uniform-datapath chain costs ~8 cycles per
+        // instruction (ncu: ~50 instructions = 410 cycles per K block with both operands in one warp),
+        // which bounded every layer whose K block holds less than ~400 cycles of tensor work.
+        if (p.a_im2col == 1) produce_a<1, BK, STAGES>(p, &tmap_a, smem_a, full_bar, empty_bar, total_tiles, n_tiles);
+        else if (p.a_im2col == 2) produce_a<2, BK, STAGES>(p, &tmap_a, smem_a, full_bar, empty_bar, total_tiles, n_tiles);
+        else produce_a<0, BK, STAGES>(p, &tmap_a, smem_a, full_bar, empty_bar, total_tiles, n_tiles);
+    } else if (warp == kWarpB) {
+        // ===================== B-operand TMA producer =====================
+        // weights [N][R*S*C]: the K offset of tap (r, s), channel block cb is kb * BK (C == cblocks * BK)
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
-        const int pq = p.P * p.Q;
-        const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b), full_base = smem_u32(full_bar);
+        const uint32_t b_base = smem_u32(smem_b), full_base = smem_u32(full_bar);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * kBM, n0 = (tile % n_tiles) * BN;
-            int wq = 0, hp = 0, nb = 0;
-            if (p.a_im2col == 1) {                 // first output pixel of the tile -> input coords
-                nb = m0 / pq;
-                const int rem = m0 - nb * pq;
-                hp = rem / p.Q;
-                wq = rem - hp * p.Q;
-            }
-            if (p.a_im2col == 2) {                 // patch -> (image, first output row, first output column)
-                const int mt = tile / n_tiles, per_img = p.tiles_p * p.tiles_q;
-                nb = mt / per_img;
-                const int rem = mt - nb * per_img;
-                hp = (rem / p.tiles_q) * p.TH;
-                wq = (rem % p.tiles_q) * p.TW;
-            }
-            const int w0 = wq * p.stride_w - p.pad_w, h0 = hp * p.stride_h - p.pad_h;
-            int r = 0, s = 0, cb = 0;
+            const int n0 = (n_tiles == 1 ? 0 : tile % n_tiles) * BN;
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(empty_bar + stage, phase ^ 1);
                 if (leader) {
                     const uint32_t bar = full_base + (uint32_t)stage * 8u;
-                    const uint32_t dst_a = a_base + (uint32_t)stage * (uint32_t)Cfg::kABytes;
-                    const uint32_t dst_b = b_base + (uint32_t)stage * (uint32_t)Cfg::kBBytes;
-                    mbar_expect_tx_a(bar, Cfg::kStageBytes);
-                    if (p.a_im2col == 2)               // filter row kb: padded input row = p * stride_h + kb
-                        tma_load_5d_a(&tmap_a, bar, dst_a, 0, wq, hp + kb / p.stride_h, kb % p.stride_h, nb);
-                    else if (p.a_im2col)
-                        tma_load_im2col_4d_a(&tmap_a, bar, dst_a, cb * BK, w0, h0, nb, (uint16_t)s, (uint16_t)r);
-                    else
-                        tma_load_2d_a(&tmap_a, bar, dst_a, kb * BK, m0);
-                    // weights [N][R*S*C]: the K offset of tap (r, s), channel block cb is kb * BK (C == cblocks * BK)
-                    tma_load_2d_a(&tmap_b, bar, dst_b, kb * BK, n0);
+                    mbar_expect_tx_a(bar, Cfg::kBBytes);
+                    tma_load_2d_a(&tmap_b, bar, b_base + (uint32_t)stage * (uint32_t)Cfg::kBBytes, kb * BK, n0);
                 }
-                __syncwarp();
-                if (++cb == p.cblocks) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -702,7 +734,7 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __syncwarp();
             if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
         }
-    } else {
+    } else if (warp < kWarpB) {
         // ===================== epilogue (warps 2..17) =====================
         // compile-time variants: POS = right shift by rs >= 1 (the usual case), FAST = int8 output only,
         // leaving through the staged TMA store (the int8 pipeline); anything else takes the generic body
@@ -854,7 +886,7 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
             if (++stage == rp.stages) { stage = 0; phase ^= 1; }
             if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
         }
-    } else {
+    } else if (warp < kWarpB) {                        // (warp kWarpB idles: the weights are resident here)
         const bool fast = fast_epi;
         if (p.rs >= 1) {
             if (fast) epilogue<BN, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
