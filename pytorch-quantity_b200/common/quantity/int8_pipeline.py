@@ -54,12 +54,20 @@ class _LazyConv:
 
 class _LazyAdd:
     """A NewAdd whose kernel has not run yet: it runs when the first consumer asks for a payload, by
-    which time it is known whether an nn.ReLU sits between the Eltwise and that consumer."""
+    which time it is known whether an nn.ReLU sits between the Eltwise and that consumer.
 
-    def __init__(self, x, y, q_bit):
+    It also writes only the payloads somebody reads.  The exact int16 sum is needed by an identity
+    shortcut (the next NewAdd) or a de-quantising consumer; the int8 requantisation by convolutions.  Which
+    of the two a given Eltwise feeds is a property of the (static) model, so the module keeps a census of
+    the kinds requested in earlier forwards (``mod._pipe_seen``) and the kernel skips the other output --
+    at the end of a ResNet stage nobody reads the int16 sum, which saves 2 of 6 bytes per element there.
+    A request for a kind that was not produced simply re-runs the kernel with both (first forward only)."""
+
+    def __init__(self, x, y, q_bit, mod=None):
         self.x, self.y = x, y                          # operand QTensors (not yet materialised)
         self.q_bit = q_bit
-        self.done = {}                                 # relu -> (s16, q8)
+        self.mod = mod
+        self.done = {}                                 # relu -> {"s16": tensor, "q8": tensor}
 
     @staticmethod
     def _fusable(t):
@@ -67,22 +75,39 @@ class _LazyAdd:
         return FUSE_ADD_INTO_CONV and lc is not None and lc.out is None and not t.relu_pending and not lc.mod._fuse_relu \
             and lc.mod.Conv.out_channels % 16 == 0
 
-    def get(self, relu):
-        if relu not in self.done:
+    def get(self, relu, kind):
+        """kind: "s16" (exact sum) or "q8" (Quantity(q_bit) of it).  Returns the dict of payloads held."""
+        seen = getattr(self.mod, "_pipe_seen", None) if self.mod is not None else None
+        have = self.done.get(relu)
+        if have is None or kind not in have:
+            wants = set(seen) if seen else set()
+            wants.add(kind)
+            if have:                                   # a second kind after all: produce both
+                wants = {"s16", "q8"}
+            want16, want8 = "s16" in wants, "q8" in wants
             x, y = self.x, self.y
             if not self._fusable(x) and self._fusable(y):
                 x, y = y, x
-            if self._fusable(x):                       # conv + add (+ relu) in one kernel
+            if self._fusable(x):                       # conv + add (+ relu) in one kernel (always writes int8)
                 lc = x._lazy_conv
                 mod, conv = lc.mod, lc.mod.Conv
                 sc, sc_bit, sc_relu = _operand(y)
-                self.done[relu] = _native.conv2d_s8_add(lc.q, mod._w_krsc, mod._bias_i32, conv.stride, conv.padding,
-                                                        mod.rs_bit, mod.output_bit, sc, sc_bit, sc_relu, self.q_bit,
-                                                        relu, c_real=conv.in_channels)
+                s16, q8 = _native.conv2d_s8_add(lc.q, mod._w_krsc, mod._bias_i32, conv.stride, conv.padding,
+                                                mod.rs_bit, mod.output_bit, sc, sc_bit, sc_relu, self.q_bit,
+                                                relu, want16=want16, c_real=conv.in_channels)
             else:
                 (a, abit, arelu), (b, bbit, brelu) = _operand(x), _operand(y)
-                self.done[relu] = _native.add_requant(a, abit, arelu, b, bbit, brelu, self.q_bit, out_relu=relu)
-        return self.done[relu]
+                s16, q8 = _native.add_requant(a, abit, arelu, b, bbit, brelu, self.q_bit, want16=want16,
+                                              want8=want8, out_relu=relu)
+            have = {}
+            if s16 is not None:
+                have["s16"] = s16
+            if q8 is not None:
+                have["q8"] = q8
+            self.done[relu] = have
+        if seen is not None:
+            seen.add(kind)
+        return have
 
 
 class _LazyCat:
@@ -129,6 +154,7 @@ class QTensor(torch.Tensor):
 
     def __init__(self, shape, device, q8=None, q8_bit=None, s16=None, s16_bit=None, relu_pending=False,
                  nonneg=False, lazy=None, lazy_conv=None, lazy_cat=None):
+        self.channels = int(shape[1])                  # plain attribute: tensor.shape on a subclass costs a dispatch
         self._q8, self.q8_bit = q8, q8_bit             # int8 NHWC, value = q8 / 2^q8_bit (after pending relu)
         self._s16, self.s16_bit = s16, s16_bit         # int16 NHWC exact value (outputs of NewAdd)
         self.relu_pending = relu_pending               # a ReLU was applied logically but not to the payloads
@@ -142,24 +168,31 @@ class QTensor(torch.Tensor):
         """Fractional bit of the most exact payload, without materialising anything."""
         return self.s16_bit if self.s16_bit is not None else self.q8_bit
 
-    def _materialize(self):
+    def _materialize(self, kind):
         if self._lazy_conv is not None:
             self._q8 = self._lazy_conv.get()
             self._lazy_conv = None
-        if self._lazy is not None:
+        if self._lazy is not None and (self._s16 if kind == "s16" else self._q8) is None:
             relu = self.relu_pending
-            self._s16, self._q8 = self._lazy.get(relu)  # the pending ReLU is applied by the add kernel
+            have = self._lazy.get(relu, kind)           # the pending ReLU is applied by the add kernel
+            self._s16, self._q8 = have.get("s16"), have.get("q8")   # one provenance: never mix relu / non-relu
+            self._q8_relu = None
             self.nonneg = self.nonneg or relu
-            self._lazy = None
+
+    def has_q8(self):
+        """An int8 payload exists or can be produced (no kernel runs)."""
+        return self._q8 is not None or self._lazy is not None or self._lazy_conv is not None
 
     @property
     def q8(self):
-        self._materialize()
+        self._materialize("q8")
         return self._q8
 
     @property
     def s16(self):
-        self._materialize()
+        if self.s16_bit is None:
+            return None
+        self._materialize("s16")
         return self._s16
 
     def __repr__(self):
@@ -169,7 +202,7 @@ class QTensor(torch.Tensor):
     # ---- payload access -------------------------------------------------------------------
     def int8_payload(self):
         """int8 NHWC with any pending ReLU applied (materialised once)."""
-        self._materialize()
+        self._materialize("q8")
         if not self.relu_pending or self.nonneg:
             return self.q8
         if self._q8_relu is None:
@@ -181,8 +214,7 @@ class QTensor(torch.Tensor):
         if self._lazy_cat is not None:
             v = self._lazy_cat.dequantize()
             return torch.relu(v) if self.relu_pending else v
-        self._materialize()
-        if self.s16 is not None:
+        if self.s16_bit is not None:
             v = self.s16.to(torch.float32) * (2.0 ** -self.s16_bit)
         else:
             v = self.q8.to(torch.float32) * (2.0 ** -self.q8_bit)
@@ -264,7 +296,7 @@ def _maxpool(x, kernel_size, stride=None, padding=0, dilation=1, ceil_mode=False
     k, s, p = _pair(kernel_size), _pair(stride if stride is not None else kernel_size), _pair(padding)
     if k[0] != k[1] or s[0] != s[1] or p[0] != p[1] or _pair(dilation) != (1, 1) or ceil_mode or return_indices:
         return None
-    if x.q8 is None or x.q8.shape[-1] % 16:
+    if not x.has_q8() or x.channels % 16:               # payload channels == logical channels
         return None
     q8 = x.q8
     relu = x.relu_pending and not x.nonneg
@@ -279,12 +311,12 @@ def conv_forward(mod, x):
     cat = isinstance(x, QTensor) and x._lazy_cat is not None
     if cat:
         usable = (not mod._explicit_im2col and not getattr(mod, "_smallc", False)
-                  and x.shape[1] <= mod._c_pad and x._lazy_cat.supported(mod.input_bit))
+                  and x.channels <= mod._c_pad and x._lazy_cat.supported(mod.input_bit))
         if not usable:
             x = x.dequantize()
     elif isinstance(x, QTensor):
-        usable = (not mod._explicit_im2col and not getattr(mod, "_smallc", False) and x.q8 is not None
-                  and x.q8_bit == mod.input_bit and x.q8.shape[-1] == mod._c_pad)
+        usable = (not mod._explicit_im2col and not getattr(mod, "_smallc", False) and x.has_q8()
+                  and x.q8_bit == mod.input_bit and x.channels == mod._c_pad)
         if not usable:
             x = x.dequantize()
     if isinstance(x, QTensor) and cat:
@@ -315,11 +347,11 @@ def conv_forward(mod, x):
 
 def _operand(t):
     """(payload, bit, relu) of the most exact representation of a QTensor."""
-    s16, q8 = t.s16, t.q8                              # (materialises a lazy add, fusing its ReLU)
-    relu = t.relu_pending and not t.nonneg
-    if s16 is not None:
-        return s16, t.s16_bit, relu
-    return q8, t.q8_bit, relu
+    if t.s16_bit is not None:
+        payload, bit = t.s16, t.s16_bit                # (materialises a lazy add, fusing its ReLU)
+    else:
+        payload, bit = t.q8, t.q8_bit
+    return payload, bit, t.relu_pending and not t.nonneg
 
 
 def add_forward(mod, x, y):
@@ -333,7 +365,9 @@ def add_forward(mod, x, y):
     o_bit = max(abit, bbit)
     if not (0 <= o_bit <= 7) or o_bit - min(abit, bbit) > 7 or abs(q_bit - o_bit) > 15:
         return None
-    return QTensor(x.shape, x.device, q8_bit=q_bit, s16_bit=o_bit, lazy=_LazyAdd(x, y, q_bit))
+    if not hasattr(mod, "_pipe_seen"):
+        mod._pipe_seen = set()                         # payload kinds this Eltwise's consumers have asked for
+    return QTensor(x.shape, x.device, q8_bit=q_bit, s16_bit=o_bit, lazy=_LazyAdd(x, y, q_bit, mod))
 
 
 def enable_int8_pipeline(model, enabled=True):

@@ -597,25 +597,39 @@ __device__ __forceinline__ void produce_a(const GemmParams &p, const CUtensorMap
 {
     constexpr uint32_t kABytes = kBM * BK;
     const bool leader = elect_one();
+    const int lane = threadIdx.x & 31;
     int stage = 0; uint32_t phase = 0;
     const int pq = p.P * p.Q;
     const uint32_t a_base = smem_u32(smem_a), full_base = smem_u32(full_bar);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = n_tiles == 1 ? tile : tile / n_tiles;
-        const int m0 = mt * kBM;
-        int wq = 0, hp = 0, nb = 0;
-        if (MODE == 1) {                       // first output pixel of the tile -> input coords
-            nb = m0 / pq;
-            const int rem = m0 - nb * pq;
-            hp = rem / p.Q;
-            wq = rem - hp * p.Q;
+    // Tile -> coordinate divisions are done 32 tiles at a time, one tile per lane, and handed to the
+    // (warp-uniform) issue loop with shuffles: the divisions were 40 % of this warp's instruction stream.
+    int l_m0 = 0, l_nb = 0, l_hp = 0, l_wq = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        if ((it & 31) == 0) {
+            const int t = tile + lane * (int)gridDim.x;            // tiles beyond the end are never fetched
+            const int mt = n_tiles == 1 ? t : t / n_tiles;
+            l_m0 = mt * kBM;
+            if (MODE == 1) {                   // first output pixel of the tile -> input coords
+                l_nb = l_m0 / pq;
+                const int rem = l_m0 - l_nb * pq;
+                l_hp = rem / p.Q;
+                l_wq = rem - l_hp * p.Q;
+            }
+            if (MODE == 2) {                   // patch -> (image, first output row, first output column)
+                const int per_img = p.tiles_p * p.tiles_q;
+                l_nb = mt / per_img;
+                const int rem = mt - l_nb * per_img;
+                l_hp = (rem / p.tiles_q) * p.TH;
+                l_wq = (rem % p.tiles_q) * p.TW;
+            }
         }
-        if (MODE == 2) {                       // patch -> (image, first output row, first output column)
-            const int per_img = p.tiles_p * p.tiles_q;
-            nb = mt / per_img;
-            const int rem = mt - nb * per_img;
-            hp = (rem / p.tiles_q) * p.TH;
-            wq = (rem % p.tiles_q) * p.TW;
+        const int m0 = __shfl_sync(0xffffffffu, l_m0, it & 31);
+        int wq = 0, hp = 0, nb = 0;
+        if (MODE != 0) {
+            nb = __shfl_sync(0xffffffffu, l_nb, it & 31);
+            hp = __shfl_sync(0xffffffffu, l_hp, it & 31);
+            wq = __shfl_sync(0xffffffffu, l_wq, it & 31);
         }
         const int w0 = wq * p.stride_w - p.pad_w, h0 = hp * p.stride_h - p.pad_h;
         int r = 0, s = 0, cb = 0;

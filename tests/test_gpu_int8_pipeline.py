@@ -286,3 +286,28 @@ def test_pipeline_concat_stays_quantised(tmp_path):
         assert torch.equal(out, ref)
         enable_int8_pipeline(model, False)
         assert torch.equal(model(x), ref)
+
+
+def test_pipeline_add_writes_only_consumed_payloads(tmp_path):
+    """The payload census: after one forward every Eltwise knows which of its two outputs is read, and later
+    forwards skip the other one (stage-end adds feed only convolutions -> int8 only; the last add feeds the
+    average pool -> exact int16 only).  The output stays bit-identical."""
+    from common.quantity import NewAdd, _native, enable_int8_pipeline
+    model = _build_recon("r18", tmp_path, 2)
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(5)).cuda()
+    with torch.no_grad():
+        ref = model(x)
+        enable_int8_pipeline(model)
+        first = model(x)
+        l0 = _native.LAUNCHES.get("add_requant", 0)
+        second = model(x)
+        launches = _native.LAUNCHES.get("add_requant", 0) - l0
+    assert torch.equal(first, ref) and torch.equal(second, ref)
+    adds = [(n, m) for n, m in model.named_modules() if isinstance(m, NewAdd)]
+    assert launches == len(adds) == 8, "steady state: exactly one add kernel per Eltwise"
+    kinds = {n: frozenset(m._pipe_seen) for n, m in adds}
+    both = frozenset({"s16", "q8"})
+    assert kinds[adds[-1][0]] == frozenset({"s16"}), kinds           # feeds AvgPool2d: exact sum only
+    q8_only = [n for n, k in kinds.items() if k == frozenset({"q8"})]
+    assert len(q8_only) == 3, kinds                                  # the last block of stages 1-3
+    assert sum(1 for k in kinds.values() if k == both) == 4, kinds  # blocks followed by an identity shortcut
