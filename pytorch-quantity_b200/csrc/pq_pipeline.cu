@@ -128,6 +128,39 @@ __device__ __forceinline__ void add_load16(const void *base, size_t v, int (&out
     }
 }
 
+__device__ __forceinline__ uint2 ld_nc_u2(const uint2 *p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+// 8 consecutive operands starting at element e (e % 8 == 0): one fully coalesced 16-byte (int16) or
+// 8-byte (int8) load per lane
+template <bool IS16>
+__device__ __forceinline__ void add_load8(const void *base, size_t e, int *out)
+{
+    if (IS16) {
+        const uint4 w = ld_nc_u4(reinterpret_cast<const uint4 *>(reinterpret_cast<const int16_t *>(base) + e));
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            out[2 * j] = prmt_sx(ww[j], 0x9910u);
+            out[2 * j + 1] = prmt_sx(ww[j], 0xbb32u);
+        }
+    } else {
+        const uint2 w = ld_nc_u2(reinterpret_cast<const uint2 *>(reinterpret_cast<const int8_t *>(base) + e));
+        const uint32_t ww[2] = {w.x, w.y};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            out[4 * j] = prmt_sx(ww[j], 0x8880u);
+            out[4 * j + 1] = prmt_sx(ww[j], 0x9991u);
+            out[4 * j + 2] = prmt_sx(ww[j], 0xaaa2u);
+            out[4 * j + 3] = prmt_sx(ww[j], 0xbbb3u);
+        }
+    }
+}
+
 __device__ __forceinline__ uint32_t pack4_sat_s8(int y0, int y1, int y2, int y3)
 {
     uint32_t t, w;
@@ -153,10 +186,21 @@ add_requant_kernel(const AddParams p, size_t n)
     const int a_lo = p.a_relu ? 0 : -32768, b_lo = p.b_relu ? 0 : -32768;
     const int d = QDOWN ? -p.q_shift : 0;
     const int rc = QDOWN ? (1 << (d - 1)) - 1 : 0;
+    // A warp owns 512 consecutive elements per iteration.  When the whole block lies inside the vector
+    // part, lane l takes elements [8l, 8l+8) of each 256-element half, so that every load and store
+    // instruction of the warp covers one contiguous run (16-byte accesses with a 32-byte lane stride
+    // touched every sector twice); the ragged last block keeps 16 consecutive elements per lane.
     for (size_t v = (size_t)blockIdx.x * kPipeThreads + threadIdx.x; v < nvec; v += stride) {
         int av[16], bv[16], num[16], q[16];
-        add_load16<A16>(p.a, v, av);
-        add_load16<B16>(p.b, v, bv);
+        const bool whole = (v | 31) < nvec;                                // warp-uniform
+        const size_t e0 = ((v >> 5) << 9) + ((v & 31) << 3), e1 = e0 + 256;
+        if (whole) {
+            add_load8<A16>(p.a, e0, av); add_load8<A16>(p.a, e1, av + 8);
+            add_load8<B16>(p.b, e0, bv); add_load8<B16>(p.b, e1, bv + 8);
+        } else {
+            add_load16<A16>(p.a, v, av);
+            add_load16<B16>(p.b, v, bv);
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             int x = av[j], y = bv[j];
@@ -169,13 +213,19 @@ add_requant_kernel(const AddParams p, size_t n)
             uint32_t o16[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) o16[j] = __byte_perm((uint32_t)num[2 * j], (uint32_t)num[2 * j + 1], 0x5410);
-            reinterpret_cast<uint4 *>(p.out16)[2 * v] = make_uint4(o16[0], o16[1], o16[2], o16[3]);
-            reinterpret_cast<uint4 *>(p.out16)[2 * v + 1] = make_uint4(o16[4], o16[5], o16[6], o16[7]);
+            uint4 *d0 = whole ? reinterpret_cast<uint4 *>(p.out16 + e0) : reinterpret_cast<uint4 *>(p.out16) + 2 * v;
+            uint4 *d1 = whole ? reinterpret_cast<uint4 *>(p.out16 + e1) : d0 + 1;
+            *d0 = make_uint4(o16[0], o16[1], o16[2], o16[3]);
+            *d1 = make_uint4(o16[4], o16[5], o16[6], o16[7]);
         }
-        if (p.out8)
-            reinterpret_cast<uint4 *>(p.out8)[v] =
-                make_uint4(pack4_sat_s8(q[0], q[1], q[2], q[3]), pack4_sat_s8(q[4], q[5], q[6], q[7]),
-                           pack4_sat_s8(q[8], q[9], q[10], q[11]), pack4_sat_s8(q[12], q[13], q[14], q[15]));
+        if (p.out8) {
+            const uint2 lo8 = make_uint2(pack4_sat_s8(q[0], q[1], q[2], q[3]), pack4_sat_s8(q[4], q[5], q[6], q[7]));
+            const uint2 hi8 = make_uint2(pack4_sat_s8(q[8], q[9], q[10], q[11]), pack4_sat_s8(q[12], q[13], q[14], q[15]));
+            uint2 *d0 = whole ? reinterpret_cast<uint2 *>(p.out8 + e0) : reinterpret_cast<uint2 *>(p.out8) + 2 * v;
+            uint2 *d1 = whole ? reinterpret_cast<uint2 *>(p.out8 + e1) : d0 + 1;
+            *d0 = lo8;
+            *d1 = hi8;
+        }
     }
     const size_t t = (nvec << 4) + (size_t)blockIdx.x * kPipeThreads + threadIdx.x;
     if (t < n) {
