@@ -26,32 +26,38 @@ relu_s8_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec, 
     if (t < n) yt[t] = xt[t] > 0 ? xt[t] : (int8_t)0;
 }
 
-// int8 NHWC max-pool: one thread per (output pixel, 16 channels)
+// int8 NHWC max-pool.  grid = (output rows, images); the threads of a block walk the (output column, 16-channel
+// group) pairs of one output row, channel group fastest, so a warp reads contiguous runs of the k input rows and
+// nothing is divided per element (the flat-index version spent ~400 instructions per output on 64-bit div / mod).
 __global__ void __launch_bounds__(kPipeThreads)
 maxpool_nhwc_s8_kernel(const int8_t *__restrict__ x, int8_t *__restrict__ y, int N, int H, int W, int C, int k,
                        int stride, int pad, int P, int Q, int relu)
 {
     const int cv = C >> 4;
-    const size_t total = (size_t)N * P * Q * cv;
-    for (size_t t = (size_t)blockIdx.x * kPipeThreads + threadIdx.x; t < total; t += (size_t)gridDim.x * kPipeThreads) {
-        const int c16 = (int)(t % cv);
-        size_t pix = t / cv;
-        const int q = (int)(pix % Q); pix /= Q;
-        const int pp = (int)(pix % P);
-        const size_t n = pix / P;
-        const uint32_t init = relu ? 0u : 0x80808080u;           // -128 per byte == -inf padding
+    const int pp = blockIdx.x;
+    const size_t n = blockIdx.y;
+    const int items = Q * cv;
+    const uint32_t init = relu ? 0u : 0x80808080u;               // -128 per byte == -inf padding
+    const int8_t *xin = x + n * (size_t)H * W * C;
+    int8_t *yout = y + (n * P + pp) * (size_t)Q * C;
+    int q = (int)threadIdx.x / cv, c16 = (int)threadIdx.x - q * cv;
+    const int dq = kPipeThreads / cv, dc = kPipeThreads - dq * cv;   // advance of (q, c16) per loop trip
+    for (int t = threadIdx.x; t < items; t += kPipeThreads) {
         uint4 m = make_uint4(init, init, init, init);
         for (int r = 0; r < k; ++r) {
             const int iy = pp * stride - pad + r;
             if ((unsigned)iy >= (unsigned)H) continue;
+            const int8_t *row = xin + (size_t)iy * W * C + c16 * 16;
             for (int s = 0; s < k; ++s) {
                 const int ix = q * stride - pad + s;
                 if ((unsigned)ix >= (unsigned)W) continue;
-                const uint4 v = *reinterpret_cast<const uint4 *>(x + ((n * H + iy) * W + ix) * C + c16 * 16);
+                const uint4 v = *reinterpret_cast<const uint4 *>(row + (size_t)ix * C);
                 m.x = __vmaxs4(m.x, v.x); m.y = __vmaxs4(m.y, v.y); m.z = __vmaxs4(m.z, v.z); m.w = __vmaxs4(m.w, v.w);
             }
         }
-        *reinterpret_cast<uint4 *>(y + ((n * P + pp) * Q + q) * C + c16 * 16) = m;
+        *reinterpret_cast<uint4 *>(yout + (size_t)q * C + c16 * 16) = m;
+        q += dq; c16 += dc;
+        if (c16 >= cv) { c16 -= cv; ++q; }
     }
 }
 
@@ -328,7 +334,8 @@ extern "C" int pq_maxpool_nhwc_s8(const int8_t *x, int8_t *y, int N, int H, int 
     if (!al16(x) || !al16(y)) return PQ_EALIGN;
     const int P = (H + 2 * pad - k) / stride + 1, Q = (W + 2 * pad - k) / stride + 1;
     if (P <= 0 || Q <= 0) return PQ_EINVAL;
-    pq::maxpool_nhwc_s8_kernel<<<pipe_grid((size_t)N * P * Q * (C >> 4)), pq::kPipeThreads, 0, (cudaStream_t)stream>>>(
+    if (N > 65535) return PQ_EUNSUPPORTED;
+    pq::maxpool_nhwc_s8_kernel<<<dim3((unsigned)P, (unsigned)N), pq::kPipeThreads, 0, (cudaStream_t)stream>>>(
         x, y, N, H, W, C, k, stride, pad, P, Q, relu);
     return (int)cudaGetLastError();
 }
