@@ -391,6 +391,33 @@ def gen_tiny():
     _save("tiny_e2e.npz", **arrays)
 
 
+def gen_lenet():
+    """The reference's LeNet example (quantity/test/lenet_quantity.py + lenet_reconstruction.py) on synthetic
+    MNIST-shaped inputs: single input channel, 5x5 kernel, three stacked Linear layers, no BatchNorm."""
+    import torch
+    ref_loader.install_shims()
+    sys.path.insert(0, ref_loader.REF_QUANTITY)   # model.lenet imports common.quantity (the reference's here)
+    spec = importlib.util.spec_from_file_location("pq_lenet", os.path.join(PKG, "model", "lenet", "lenet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["pq_lenet"] = mod                 # the reference torch.save()s the whole reconstructed model
+    spec.loader.exec_module(mod)
+
+    def build():
+        torch.manual_seed(5)
+        return mod.Cnn(1, 10).eval()
+
+    batches = mod.lenet_batches(4, 8, seed=1)
+    eval_batch = mod.lenet_batches(1, 16, seed=77)[0][0]
+    res, arrays = _run_reference_pipeline(build, batches, (1, 1, 28, 28), eval_batch, "lenet", worker_num=2)
+    for k, v in build().state_dict().items():
+        arrays["state/" + k] = v.numpy()
+    for i, (img, _) in enumerate(batches):
+        arrays["batch%d" % i] = img.numpy()
+    arrays["eval_batch"] = eval_batch.numpy()
+    arrays["json"] = np.frombuffer(json.dumps(res).encode(), dtype=np.uint8)
+    _save("lenet_e2e.npz", **arrays)
+
+
 def gen_r18_224():
     """BASELINE.json configs[0] (C1): ResNet-18 224x224, 64 images as 8 batches of 8,
     the reference's CPU path in full.  Only tables / bits / histograms are kept."""
@@ -425,7 +452,7 @@ def gen_r18_224():
 
 
 SECTIONS = {"stats": gen_stats, "kl": gen_kl, "fakequant": gen_fakequant, "intsim": gen_intsim,
-            "tiny": gen_tiny, "r18_224": gen_r18_224}
+            "tiny": gen_tiny, "lenet": gen_lenet, "r18_224": gen_r18_224}
 
 if __name__ == "__main__":
     assert ref_loader.available(), "needs /root/reference"

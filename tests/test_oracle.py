@@ -280,3 +280,49 @@ def test_absmax_per_channel_oracle_consistency(oracle):
     assert pc.max() == oracle.absmax_update(0, x)
     w = rng.standard_normal((7, 3, 3, 3)).astype(np.float32)
     assert np.array_equal(oracle.absmax_per_channel(w, 0), np.abs(w).reshape(7, -1).max(axis=1))
+
+
+def test_lenet_calibration_tables(oracle):
+    """The reference's LeNet example: oracle calibration on the reference's hooked tensors reproduces its
+    intervals, histograms, thresholds, bits and feat.table (no merge groups, no BatchNorm)."""
+    g = load_golden("lenet_e2e.npz")
+    j = golden_json(g)
+    net_info = j["net_info"]
+    top = ["image"] + list(net_info)
+    batches = []
+    while "feat%d/image" % len(batches) in g.files:
+        batches.append({n: g["feat%d/%s" % (len(batches), n)] for n in top})
+    assert len(batches) == 4 and j["merge_groups"] == []
+    r = oracle.calibrate(batches, top, net_info, j["merge_groups"], return_all=True)
+    assert r["raw_bits"] == j["raw_bits"]
+    for n in top:
+        assert float(r["intervals"][n]) == j["intervals"][n]
+        assert float(r["thresholds"][n]) == j["thresholds"][n]
+        assert np.array_equal(np.asarray(r["dists"][n], dtype=np.float64), g["dist/" + n].astype(np.float64))
+    lines = oracle.feat_table_lines(top, j["cared_op_layer_names"], net_info, r["bits"])
+    assert "\n".join(lines) + "\n" == j["after_weight_quantize"]["feat.table"]
+
+
+def test_lenet_integer_layers(oracle):
+    """ReconModel of LeNet layer by layer from the oracle's NewConv2d / NewLinear restatements: a 1-channel 3x3
+    conv, a 5x5 conv on 6 channels (fed through ReLU + max-pool of the reference's own output) and the three
+    stacked Linear layers (each fed with the reference's output of the previous one)."""
+    import torch
+    import torch.nn.functional as F
+    g = load_golden("lenet_e2e.npz")
+    info = golden_json(g)["quantity_information"]
+    sd = {k[len("state/"):]: g[k] for k in g.files if k.startswith("state/")}
+    x = g["eval_batch"]
+    y0, _ = oracle.int_conv_layer(x, sd["conv.0.weight"], sd["conv.0.bias"], info["conv.0"], stride=1, padding=1)
+    assert np.array_equal(y0, g["ReconModel/layer/conv.0"])
+    p0 = F.max_pool2d(torch.relu(torch.from_numpy(g["ReconModel/layer/conv.0"])), 2, 2).numpy()
+    y1, _ = oracle.int_conv_layer(p0, sd["conv.3.weight"], sd["conv.3.bias"], info["conv.3"], stride=1, padding=0)
+    assert np.array_equal(y1, g["ReconModel/layer/conv.3"])
+    p1 = F.max_pool2d(torch.relu(torch.from_numpy(g["ReconModel/layer/conv.3"])), 2, 2).numpy().reshape(x.shape[0], -1)
+    prev = p1
+    for name in ("fc.0", "fc.1", "fc.2"):
+        out = oracle.int_linear_layer(prev, sd[name + ".weight"], sd[name + ".bias"], info[name])
+        out = out[0] if isinstance(out, tuple) else out
+        assert np.array_equal(out, g["ReconModel/layer/" + name]), name
+        prev = g["ReconModel/layer/" + name]
+    assert np.array_equal(prev, g["ReconModel/y"])
