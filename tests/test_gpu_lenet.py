@@ -143,3 +143,55 @@ def test_lenet_recontest_outputs(tmp_path):
         s = o * 2.0 ** info[name]["output_bit"]
         assert np.array_equal(s, np.rint(s)) and np.abs(s).max() <= 128
     assert np.abs(y - g["ReconTest/y"]).max() <= 8 * 2.0 ** -info["fc.2"]["output_bit"]
+
+
+# ------------------------------------------------------------------ example drivers (quantity/test/*.py counterparts)
+EXAMPLES = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pytorch-quantity_b200", "test")
+
+
+@pytest.mark.parametrize("model", ["lenet", "resnet18_cifar"])
+def test_example_drivers_run(tmp_path, model):
+    """quantity_example.py then reconstruction_example.py, as a user would run them (separate processes, tables
+    and JSON passed through the work directory)."""
+    import subprocess
+    import sys
+    wd = str(tmp_path / "workdir")
+    r = subprocess.run([sys.executable, "quantity_example.py", "--model", model, "--batches", "3", "--batch", "4",
+                        "--workdir", wd], cwd=EXAMPLES, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    table = open(os.path.join(wd, "feat.table")).read().strip().split("\n")
+    assert table[0].startswith("image ") and len(table) > 5
+    assert os.path.isdir(os.path.join(wd, "new_weight")) and os.listdir(os.path.join(wd, "new_bias"))
+    r = subprocess.run([sys.executable, "reconstruction_example.py", "--model", model, "--batches", "2", "--batch", "8",
+                        "--workdir", wd, "--int8-pipeline"], cwd=EXAMPLES, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for line in ("origin model", "merge bn model", "reconstruction model", "q-dq reconstruction model"):
+        assert line in r.stdout, r.stdout[-2000:]
+    assert os.path.exists(os.path.join(wd, "quantity_model.pth"))
+
+
+def test_cifar_resnet18_pipeline_equals_fp32_boundary(tmp_path):
+    """The reference's own model (CIFAR ResNet-18, 32x32): 4x4 feature maps in the last stage, M smaller than one
+    128-row tile per image; int8 pipeline == fp32-boundary ReconModel bit for bit."""
+    import sys
+    sys.path.insert(0, EXAMPLES)
+    import _models
+    import tools
+    from common.quantity import enable_int8_pipeline, merge_bn
+    net, shape = _models.build("resnet18_cifar")
+    data = _models.batches(shape, 3, 8)
+    cfg, user = _models.configs(str(tmp_path / "wd"), shape, len(data))
+    with torch.no_grad():
+        q = tools.Quantity(merge_bn(net, "cpu"), config=cfg, user_config=user, verbose=False)
+        q.activation_quantize(data)
+        q.weight_quantize()
+        net2, _ = _models.build("resnet18_cifar")
+        r = tools.Reconstruction(net2, config=cfg)
+        r.merge_bn()
+        model = r.ReconModel(r.get_quantity_information(), None).cuda().eval()
+        x = _models.batches(shape, 1, 37, seed=500)[0][0].cuda()
+        ref = model(x)
+        enable_int8_pipeline(model)
+        assert torch.equal(model(x), ref)
+        assert torch.equal(model(x), ref)              # second forward: payload census in steady state
+    assert torch.isfinite(ref).all() and ref.shape == (37, 10)
