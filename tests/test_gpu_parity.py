@@ -282,6 +282,18 @@ def test_abi_error_codes(cq):
     assert lib.pq_hist2048_multi_f32(ptrs, ns, iv, 1, h.data_ptr(), None) == -1                  # interval <= 0
     with pytest.raises(RuntimeError):
         cq.QuanDequan(8, 3)(torch.zeros(4))                                                       # CPU tensor: no fallback
+    # per-channel max-abs (extension): empty is a no-op, more than 8192 channels / misaligned pointers are refused
+    bits = torch.zeros(16, dtype=torch.int32, device="cuda")
+    assert lib.pq_absmax_per_channel_f32(None, 0, 4, 10, bits.data_ptr(), None) == 0
+    assert lib.pq_absmax_per_channel_f32(x.data_ptr(), 1, 8193, 1, bits.data_ptr(), None) == -2
+    assert lib.pq_absmax_per_channel_f32(x.data_ptr() + 2, 1, 2, 2, bits.data_ptr(), None) == -3
+    assert lib.pq_absmax_per_channel_f32(x.data_ptr(), 1, 2, 4, None, None) == -1
+    assert not bits.any()
+    # int8 max-pool: channel count must be a multiple of 16, padding smaller than the window
+    q = torch.zeros((1, 4, 4, 16), dtype=torch.int8, device="cuda")
+    assert lib.pq_maxpool_nhwc_s8(q.data_ptr(), q.data_ptr(), 1, 4, 4, 8, 2, 2, 0, 0, None) == -2
+    assert lib.pq_maxpool_nhwc_s8(q.data_ptr(), q.data_ptr(), 1, 4, 4, 16, 2, 2, 2, 0, None) == -2
+    assert lib.pq_maxpool_nhwc_s8(q.data_ptr(), q.data_ptr(), 0, 4, 4, 16, 2, 2, 0, 0, None) == -1
 
 
 # ---------------------------------------------------------------- per-channel max-abs (extension of a1)
