@@ -22,7 +22,7 @@ __device__ __forceinline__ uint32_t pack2_s16(int hi, int lo)
 }
 __device__ __forceinline__ int mulhi(int a, int b) { return __mulhi(a, b); }
 
-struct P { int half, sh, mulsh, lo; int bias[16]; uint32_t bias2[8]; };
+struct P { int half, sh, mulsh, lo; int bias[16]; uint32_t bias2[8]; int c[16], h[16], l[16]; };
 
 // A: current chain (all ALU pipe)
 __device__ __forceinline__ void chain_a(const int (&acc)[16], const P &p, uint32_t (&out)[4])
@@ -98,7 +98,65 @@ __device__ __forceinline__ void chain_f(const int (&acc)[16], const P &p, uint32
 #pragma unroll
     for (int j = 0; j < 4; ++j) out[j] = pack4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
 }
-// G: float tail -- r (after the integer shift) -> float via the magic-number add is NOT exact in general; here
+// G: bias folded into the rounding add (per-channel c), both saturations as min(h) / max(l) (three constant vectors)
+__device__ __forceinline__ void chain_g(const int (&acc)[16], const P &p, uint32_t (&out)[4])
+{
+    int y[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int t = (acc[j] + p.c[j] + (acc[j] >> 31)) >> p.sh;
+        y[j] = max(min(t, p.h[j]), p.l[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = pack4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+}
+// H: G with a fused ReLU: min(h) and max(., 0) in one VIMNMX.RELU
+__device__ __forceinline__ void chain_h(const int (&acc)[16], const P &p, uint32_t (&out)[4])
+{
+    int y[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int t = (acc[j] + p.c[j] + (acc[j] >> 31)) >> p.sh;
+        y[j] = __vimin_s32_relu(t, p.h[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = pack4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+}
+// I: two constant vectors (c, b): max(b - 128, min(b + 127, t)) as two VIADDMNMX
+__device__ __forceinline__ void chain_i(const int (&acc)[16], const P &p, uint32_t (&out)[4])
+{
+    int y[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int t = (acc[j] + p.c[j] + (acc[j] >> 31)) >> p.sh;
+        y[j] = __viaddmax_s32(p.bias[j], -128, __viaddmin_s32(p.bias[j], 127, t));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = pack4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+}
+// J: I with a fused ReLU: one VIADDMNMX.RELU
+__device__ __forceinline__ void chain_j(const int (&acc)[16], const P &p, uint32_t (&out)[4])
+{
+    int y[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int t = (acc[j] + p.c[j] + (acc[j] >> 31)) >> p.sh;
+        y[j] = __viaddmin_s32_relu(p.bias[j], 127, t);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = pack4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+}
+// K: only the shift part (VIADD, LEA.HI.SX32, SHF) + pack: the floor of any formulation that keeps this rounding
+__device__ __forceinline__ void chain_k(const int (&acc)[16], const P &p, uint32_t (&out)[4])
+{
+    int y[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = (acc[j] + p.c[j] + (acc[j] >> 31)) >> p.sh;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = pack4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+}
+// (a float tail -- r after the integer shift -> float via the magic-number add -- is NOT exact in general and is
+// not a candidate for the product) -- r (after the integer shift) -> float via the magic-number add is NOT exact in general; here
 // only to see the fma-pipe rate of a FADD/FMNMX mix (not a candidate for the product)
 template <int V>
 __global__ void __launch_bounds__(512, 1) bench(const int *in, uint32_t *out, P p, int iters, long long *cycles, int one)
@@ -115,6 +173,11 @@ __global__ void __launch_bounds__(512, 1) bench(const int *in, uint32_t *out, P 
         if (V == 3) chain_d(acc, p, o);
         if (V == 4) chain_e(acc, p, o, one);
         if (V == 5) chain_f(acc, p, o, one);
+        if (V == 6) chain_g(acc, p, o);
+        if (V == 7) chain_h(acc, p, o);
+        if (V == 8) chain_i(acc, p, o);
+        if (V == 9) chain_j(acc, p, o);
+        if (V == 10) chain_k(acc, p, o);
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] += (int)o[j & 3];                   // 1 extra op per element, the same for every variant
     }
@@ -132,10 +195,17 @@ int main()
     cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
     P p; p.sh = 9; p.half = 1 << 8; p.mulsh = 1 << (32 - 9); p.lo = -128;
     for (int j = 0; j < 16; ++j) p.bias[j] = j * 7 - 50;
+    for (int j = 0; j < 16; ++j) {
+        p.c[j] = p.half + p.bias[j] * (1 << p.sh);
+        p.h[j] = p.bias[j] + 127 < 127 ? p.bias[j] + 127 : 127;
+        p.l[j] = p.bias[j] - 128 > -128 ? p.bias[j] - 128 : -128;
+    }
     for (int j = 0; j < 8; ++j) p.bias2[j] = ((uint32_t)(uint16_t)(int16_t)p.bias[2 * j + 1] << 16) | (uint16_t)(int16_t)p.bias[2 * j];
     const int iters = 20000;
-    const char *names[6] = {"A current (ALU only)", "", "C IMAD.HI sign+shift", "D s16x2 tail", "E IMAD.HI + s16x2", "F IMAD +half"};
-    for (int v = 0; v < 6; ++v) {
+    const char *names[11] = {"A current (ALU only)", "", "C IMAD.HI sign+shift", "D s16x2 tail", "E IMAD.HI + s16x2", "F IMAD +half",
+                             "G folded bias, min h max l", "H folded bias, min.relu", "I folded, 2x VIADDMNMX", "J folded, VIADDMNMX.RELU",
+                             "K shift + pack only"};
+    for (int v = 0; v < 11; ++v) {
         if (v == 1) continue;
         for (int rep = 0; rep < 2; ++rep) {
             switch (v) {
@@ -144,6 +214,11 @@ int main()
                 case 3: bench<3><<<148, 512>>>(in, out, p, iters, cyc, 1); break;
                 case 4: bench<4><<<148, 512>>>(in, out, p, iters, cyc, 1); break;
                 case 5: bench<5><<<148, 512>>>(in, out, p, iters, cyc, 1); break;
+                case 6: bench<6><<<148, 512>>>(in, out, p, iters, cyc, 1); break;
+                case 7: bench<7><<<148, 512>>>(in, out, p, iters, cyc, 1); break;
+                case 8: bench<8><<<148, 512>>>(in, out, p, iters, cyc, 1); break;
+                case 9: bench<9><<<148, 512>>>(in, out, p, iters, cyc, 1); break;
+                case 10: bench<10><<<148, 512>>>(in, out, p, iters, cyc, 1); break;
             }
             cudaDeviceSynchronize();
         }
