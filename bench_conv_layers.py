@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--s8-out", action="store_true", help="store int8 NHWC instead of fp32 NCHW")
     ap.add_argument("--only", type=int, default=None, help="run only this row of the table (for ncu captures)")
     ap.add_argument("--fused-add", action="store_true", help="conv + NewAdd + ReLU in one kernel (int16 shortcut)")
+    ap.add_argument("--classic-bias", action="store_true", help="plain int32 bias (no PQ_FLAG_BIAS_FOLDED constants)")
     args = ap.parse_args()
     B = args.batch
     tot_conv = tot_q = tot_ops = 0.0
@@ -52,6 +53,8 @@ def main():
         wk = torch.randint(-128, 127, (cout, k, k, cpad), dtype=torch.int8, device="cuda")
         wk[..., cin:] = 0
         bias = torch.randint(-128, 127, (cout,), dtype=torch.int32, device="cuda")
+        if not args.classic_bias:
+            bias = _native.bias_fold(bias, 9)          # what NewConv2d / NewLinear hold (rs = 9 below)
         P = (h + 2 * pad - k) // s + 1
         if cin <= 8 and not plain and s % 2 == 0:      # windowed small-channel convolution (the stem)
             w8 = torch.zeros((cout, k, 8, 8), dtype=torch.int8, device="cuda")

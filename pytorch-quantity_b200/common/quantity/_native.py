@@ -48,8 +48,10 @@ SYMBOLS = {
     "pq_add_requant": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _sz, _vp, _vp, _i, _vp]),
     "pq_add_requant_ex": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _sz, _i, _vp, _vp, _i, _vp]),
     "pq_concat_requant_s8": (_i, [_vp, _i, _sz, _i, _i, _vp, _vp]),
+    "pq_bias_fold_s32": (_i, [_vp, _i, _i, _vp, _vp]),
 }
 FLAG_RELU = 1
+FLAG_BIAS_FOLDED = 2
 
 
 class ConvDesc(ctypes.Structure):
@@ -220,6 +222,24 @@ def kl_search(counts_f64, want_curves=False):
     return thr, kl
 
 
+def bias_fold(bias_i32, rs):
+    """int32 [N] quantised bias -> int32 [2N]: the bias followed by 2^(rs-1) + (bias << rs), the per-channel
+    constant of the folded int8 epilogue (PQ_FLAG_BIAS_FOLDED, include/pq_sm100.h).  Returned unchanged when the
+    fold does not apply (N % 4 != 0 or rs outside [1, 20])."""
+    require_cuda(bias_i32, "bias_fold")
+    n = bias_i32.numel()
+    if n % 4 or bias_i32.dtype != torch.int32 or not 1 <= int(rs) <= 20:
+        return bias_i32
+    out = torch.empty(2 * n, dtype=torch.int32, device=bias_i32.device)
+    check(lib().pq_bias_fold_s32(bias_i32.contiguous().data_ptr(), n, int(rs), out.data_ptr(), _stream(bias_i32)),
+          "pq_bias_fold_s32")
+    return out
+
+
+def _bias_flags(bias_q, n, relu):
+    return (FLAG_RELU if relu else 0) | (FLAG_BIAS_FOLDED if bias_q.numel() == 2 * n else 0)
+
+
 def _flat_out(x):
     require_cuda(x, "elementwise kernel")
     if x.dtype != torch.float32:
@@ -320,7 +340,7 @@ def conv2d_smallc_s8(xp, w_krs8, bias_q, in_hw, kernel, stride, padding, rs, ob,
     out_s8 = torch.empty((N, P, Q, K), dtype=torch.int8, device=xp.device) if want_s8 else None
     with _Timed("conv_s8", 1, 2 * N * P * Q * K * R * S * (c_real or 8), xp.device):        # int8 ops
         check(lib().pq_conv2d_smallc_s8(xp.data_ptr(), w_krs8.data_ptr(), bias_q.data_ptr(), ctypes.byref(d), Hp, Wp,
-                                        FLAG_RELU if relu else 0, out_f32.data_ptr() if want_f32 else None,
+                                        _bias_flags(bias_q, K, relu), out_f32.data_ptr() if want_f32 else None,
                                         out_s8.data_ptr() if want_s8 else None, _stream(xp)), "pq_conv2d_smallc_s8")
     return out_f32, out_s8
 
@@ -338,7 +358,7 @@ def gemm_s8(a, w, bias_q, rs, ob, hw=1, want_f32=True, want_s8=False, k_real=Non
         out_s8 = torch.empty((M, N), dtype=torch.int8, device=a.device)
     with _Timed("gemm_s8", 1, 2 * M * N * (k_real or K), a.device):      # "bytes" field carries int8 ops here
         check(lib().pq_gemm_s8_ex(a.data_ptr(), w.data_ptr(), bias_q.data_ptr(), M, N, K, int(rs), int(ob), hw,
-                                  FLAG_RELU if relu else 0, out_f32.data_ptr() if want_f32 else None,
+                                  _bias_flags(bias_q, N, relu), out_f32.data_ptr() if want_f32 else None,
                                   out_s8.data_ptr() if want_s8 else None, _stream(a)), "pq_gemm_s8")
     return out_f32, out_s8
 
@@ -356,7 +376,7 @@ def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, wa
     out_s8 = torch.empty((N, P, Q, K), dtype=torch.int8, device=x_nhwc.device) if want_s8 else None
     with _Timed("conv_s8", 1, 2 * N * P * Q * K * R * S * (c_real or C), x_nhwc.device):   # int8 ops
         check(lib().pq_conv2d_s8_ex(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
-                                    FLAG_RELU if relu else 0, out_f32.data_ptr() if want_f32 else None,
+                                    _bias_flags(bias_q, K, relu), out_f32.data_ptr() if want_f32 else None,
                                     out_s8.data_ptr() if want_s8 else None, _stream(x_nhwc)), "pq_conv2d_s8")
     return out_f32, out_s8
 

@@ -138,7 +138,8 @@ class _IntSimBase(nn.Module):
         layer.weight = nn.Parameter(wq)
         layer.bias = nn.Parameter(torch.zeros(out_features, device=w.device))
         self.register_buffer("quantized_bias", bq)                      # fp32, integer-valued
-        self.register_buffer("_bias_i32", bq.to(torch.int32))
+        # [N] bias, followed (when N % 4 == 0 and 1 <= rs <= 20) by the folded constants of the int8 epilogue
+        self.register_buffer("_bias_i32", _native.bias_fold(bq.to(torch.int32), self.rs_bit))
         return wq
 
 

@@ -289,6 +289,7 @@ struct GemmParams {
     int tw_shift, TW, TH;      // output patch of one tile: TH x TW = 128 pixels, TW = 1 << tw_shift
     int tiles_p, tiles_q;      // patches per image
     const int32_t *bias;       // [N] quantised bias (already saturated to int8 range)
+    const int32_t *bias_c;     // PQ_FLAG_BIAS_FOLDED (1 <= rs <= 20): [N] 2^(rs-1) + (bias << rs), see requant_folded
     float *out_f32;            // optional
     int8_t *out_s8;            // optional, [M][N]
 };
@@ -369,7 +370,25 @@ __device__ __forceinline__ int requant_t(int acc, const Requant &q, int bias)
     return __viaddmax_s32(r, bias, q.lo);                     // max(r + bias, lo); callers saturate from above
 }
 
-template <int BN, bool POS, bool FAST, bool ADD = false>
+// The same chain with BiasAdd folded into the rounding add (PQ_FLAG_BIAS_FOLDED, rs >= 1): b << rs is a multiple
+// of 2^rs, so with the per-channel constant c = 2^(rs-1) + (b << rs)
+//   (acc + c + (acc >> 31)) >> rs  ==  round_half_away(acc / 2^rs) + b,
+// and because the rounding is monotone the first saturation can be applied to the accumulator instead, with
+// channel-independent bounds:  clamp(r, -128, 127) == r(clamp(acc, -128 * 2^rs - 2^(rs-1) + 1, 127 * 2^rs + 2^(rs-1) - 1)).
+// The second saturation is the packing instruction's.  With a fused ReLU the lower bound is redundant (anything
+// below it ends at 0 either way).  5 ALU operations per element instead of 6, with the same single per-channel
+// constant vector as the classic chain; the CPU test suite checks the identities over every (rs, b) and the
+// accumulators around both bounds.
+template <bool RELU>
+__device__ __forceinline__ int requant_folded(int acc, int sh, int a_lo, int a_hi, int c)
+{
+    const int a = RELU ? min(acc, a_hi) : max(min(acc, a_hi), a_lo);
+    const int t = (a + c + (a >> 31)) >> sh;
+    return RELU ? max(t, 0) : t;
+}
+
+// FOLD: 0 = classic chain, 1 = folded bias, 2 = folded bias + fused ReLU (FAST, non-ADD, POS only)
+template <int BN, bool POS, bool FAST, bool ADD = false, int FOLD = 0>
 __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap *tmap_o, uint8_t *smem_o,
                                          uint64_t *tmem_full_bar, uint64_t *tmem_empty_bar, uint32_t tmem_base,
                                          int total_tiles, int n_tiles)
@@ -431,6 +450,19 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
                 // N % 16 == 0 here, so a chunk is entirely inside or outside N (outside: the TMA store clips
                 // it); bias is 64-byte aligned: 4 x LDG.128, warp-uniform
                 if (n0 + c0 >= p.N) return;
+                if (FOLD != 0) {
+                    const int4 *cp = reinterpret_cast<const int4 *>(p.bias_c + n0 + c0);
+                    const int a_hi = 127 * (1 << rq.sh) + rq.half - 1, a_lo = -128 * (1 << rq.sh) - rq.half + 1;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int4 c4 = __ldg(cp + j);
+                        packed[j] = pack4_sat_s8(requant_folded<FOLD == 2>((int)a[4 * j], rq.sh, a_lo, a_hi, c4.x),
+                                                 requant_folded<FOLD == 2>((int)a[4 * j + 1], rq.sh, a_lo, a_hi, c4.y),
+                                                 requant_folded<FOLD == 2>((int)a[4 * j + 2], rq.sh, a_lo, a_hi, c4.z),
+                                                 requant_folded<FOLD == 2>((int)a[4 * j + 3], rq.sh, a_lo, a_hi, c4.w));
+                    }
+                    return;
+                }
                 const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -755,6 +787,8 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool fast = fast_epi;
         if (p.rs >= 1) {
             if (fast && p.add_sc) epilogue<BN, true, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else if (fast && p.bias_c && p.relu) epilogue<BN, true, true, false, 2>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else if (fast && p.bias_c) epilogue<BN, true, true, false, 1>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else if (fast) epilogue<BN, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else epilogue<BN, true, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
         } else {
@@ -903,7 +937,9 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
     } else if (warp < kWarpB) {                        // (warp kWarpB idles: the weights are resident here)
         const bool fast = fast_epi;
         if (p.rs >= 1) {
-            if (fast) epilogue<BN, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            if (fast && p.bias_c && p.relu) epilogue<BN, true, true, false, 2>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else if (fast && p.bias_c) epilogue<BN, true, true, false, 1>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else if (fast) epilogue<BN, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else epilogue<BN, true, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
         } else {
             if (fast) epilogue<BN, false, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
@@ -1079,6 +1115,12 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, int 
 
 namespace {
 // validates a fused-add request and copies it into the kernel parameters
+// PQ_FLAG_BIAS_FOLDED: bias_q is int32 [2][N] = bias | 2^(rs-1) + (bias << rs)   (pq_bias_fold_s32)
+void apply_bias_fold(pq::GemmParams &p, const int32_t *bias_q, int flags, int N, int rs)
+{
+    p.bias_c = ((flags & PQ_FLAG_BIAS_FOLDED) && rs >= 1 && rs <= 20 && (N & 3) == 0) ? bias_q + N : nullptr;
+}
+
 int apply_add(pq::GemmParams &p, const pq_add_desc *add, int conv_ob)
 {
     if (!add) return PQ_OK;
@@ -1138,6 +1180,7 @@ int gemm_impl(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, in
     p.M = M; p.N = N; p.num_kb = (K + bk - 1) / bk; p.a_im2col = 0;
     p.rs = rs; p.ob = ob; p.hw = hw; p.bias = bias_q; p.out_f32 = out_f32; p.out_s8 = out_s8;
     p.relu = flags & PQ_FLAG_RELU;
+    apply_bias_fold(p, bias_q, flags, N, rs);
     if ((rc = apply_add(p, add, ob)) != PQ_OK) return rc;
     return launch(ta, tb, p, bk, bn, (cudaStream_t)stream);
 }
@@ -1203,6 +1246,7 @@ int conv_impl(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
     p.P = d.P; p.Q = d.Q; p.stride_h = d.stride_h; p.stride_w = d.stride_w; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
     p.rs = d.rs; p.ob = d.ob; p.hw = d.P * d.Q; p.bias = bias_q; p.out_f32 = out_f32_nchw; p.out_s8 = out_s8_nhwc;
     p.relu = flags & PQ_FLAG_RELU;
+    apply_bias_fold(p, bias_q, flags, d.K, d.rs);
     if ((rc = apply_add(p, add, d.ob)) != PQ_OK) return rc;
     return launch(ta, tb, p, bk, bn, (cudaStream_t)stream);
 }
@@ -1242,6 +1286,7 @@ extern "C" int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const
     p.stride_h = d.stride_h; p.stride_w = d.stride_w; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
     p.rs = d.rs; p.ob = d.ob; p.hw = d.P * d.Q; p.bias = bias_q; p.out_f32 = out_f32_nchw; p.out_s8 = out_s8_nhwc;
     p.relu = flags & PQ_FLAG_RELU;
+    apply_bias_fold(p, bias_q, flags, d.K, d.rs);
     // Preferred: the row kernel (stride_w == 2: GEMM rows 16 bytes apart == an un-swizzled core matrix)
     if (d.stride_w == 2 && d.R <= 8) {
         const int n_tiles = (d.K + 63) / 64;

@@ -303,6 +303,15 @@ concat_requant_scalar_kernel(const ConcatParams p, size_t pixels, int8_t *__rest
         out[t] = (int8_t)q;
     }
 }
+__global__ void bias_fold_kernel(const int32_t *__restrict__ b, int n, int rs, int32_t *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int v = max(-128, min(127, b[i]));               // BiasAdd operands are int8-saturated (new_quantity_op.py:148)
+    out[i] = v;
+    out[n + i] = (rs >= 1 && rs <= 20) ? (1 << (rs - 1)) + v * (1 << rs) : 0;
+}
+
 }  // namespace pq
 
 namespace {
@@ -410,5 +419,14 @@ extern "C" int pq_concat_requant_s8(const pq_concat_src *srcs_host, int k, size_
     else
         pq::concat_requant_scalar_kernel<<<pipe_grid(pixels * (size_t)c_out_pad), pq::kPipeThreads, 0, st>>>(
             p, pixels, out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pq_bias_fold_s32(const int32_t *bias_q, int n, int rs, int32_t *out, pq_stream_t stream)
+{
+    if (n < 0) return PQ_EINVAL;
+    if (n == 0) return PQ_OK;
+    if (!bias_q || !out) return PQ_EINVAL;
+    pq::bias_fold_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(bias_q, n, rs, out);
     return (int)cudaGetLastError();
 }

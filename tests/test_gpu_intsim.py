@@ -182,3 +182,33 @@ def test_tiny_reconmodel_bit_exact(tmp_path):
     # the saved model loads back (classes picklable by qualified name, buffers registered)
     loaded = torch.load(str(tmp_path / "workdir" / "ReconModel.pth"), weights_only=False)
     assert np.array_equal(loaded.cuda()(torch.from_numpy(g["eval_batch"]).cuda()).cpu().numpy(), y)
+
+
+@pytest.mark.parametrize("M,N,K,rs,relu", [(1000, 64, 64, 7, True), (777, 256, 64, 9, False), (4096, 128, 256, 12, True),
+                                           (513, 32, 576, 1, False), (2048, 512, 128, 20, False), (300, 16, 32, 5, True),
+                                           (999, 64, 1024, 3, False)])
+def test_folded_bias_epilogue_equals_classic(oracle, M, N, K, rs, relu):
+    """PQ_FLAG_BIAS_FOLDED against the classic staged epilogue and the oracle, with biases at the int8 extremes and
+    accumulators that saturate both ways."""
+    from common.quantity import _native
+    rng = np.random.default_rng(M + N + rs)
+    a = rng.integers(-128, 128, size=(M, K)).astype(np.int8)
+    w = rng.integers(-128, 128, size=(N, K)).astype(np.int8)
+    a[:7] = 127; w[:5] = 127; w[5:9] = -128                        # extreme accumulators
+    bias = rng.integers(-128, 128, size=N).astype(np.int32)
+    bias[:4] = [-128, 127, 0, -1]
+    ta, tw, tb = torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(bias).cuda()
+    folded_bias = _native.bias_fold(tb, rs)
+    assert folded_bias.numel() == 2 * N and torch.equal(folded_bias[:N], tb)
+    _, classic = _native.gemm_s8(ta, tw, tb, rs, 3, want_f32=False, want_s8=True, relu=relu)
+    _, folded = _native.gemm_s8(ta, tw, folded_bias, rs, 3, want_f32=False, want_s8=True, relu=relu)
+    assert torch.equal(classic, folded)
+    acc = a.astype(np.int64) @ w.astype(np.int64).T
+    want = np.clip(oracle.right_shift(acc, rs) + bias[None, :], -128, 127)
+    if relu:
+        want = np.maximum(want, 0)
+    assert np.array_equal(folded.cpu().numpy().astype(np.int64), want)
+    # the fp32-boundary epilogue ignores the flag and reads the plain bias at the front of the buffer
+    f32a, _ = _native.gemm_s8(ta, tw, tb, rs, 3, want_f32=True, want_s8=False)
+    f32b, _ = _native.gemm_s8(ta, tw, folded_bias, rs, 3, want_f32=True, want_s8=False)
+    assert torch.equal(f32a, f32b)

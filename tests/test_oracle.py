@@ -326,3 +326,29 @@ def test_lenet_integer_layers(oracle):
         assert np.array_equal(out, g["ReconModel/layer/" + name]), name
         prev = g["ReconModel/layer/" + name]
     assert np.array_equal(prev, g["ReconModel/y"])
+
+
+def test_folded_bias_identity(oracle):
+    """The identities behind PQ_FLAG_BIAS_FOLDED (include/pq_sm100.h): BiasAdd folds into RightShift's rounding
+    add, RightShift's saturation moves to the accumulator with channel-independent bounds, and under a fused
+    ReLU the lower bound is redundant -- checked against the oracle's RightShift / BiasAdd / Sp composition."""
+    rng = np.random.default_rng(7)
+    for rs in (1, 2, 5, 9, 13, 20):
+        half = 1 << (rs - 1)
+        a_hi, a_lo = 127 * (1 << rs) + half - 1, -128 * (1 << rs) - half + 1
+        edges = np.concatenate([np.arange(-6, 7) + e for e in (a_lo, a_hi, 0, -half, half, a_lo - (1 << rs), a_hi + (1 << rs))])
+        acc = np.concatenate([edges, rng.integers(-2 ** 29, 2 ** 29, size=4000),
+                              rng.integers(-300 << rs, 300 << rs, size=4000),
+                              np.arange(-(1 << min(rs + 2, 12)), (1 << min(rs + 2, 12)) + 1)]).astype(np.int64)[:, None]
+        b = np.arange(-128, 128, dtype=np.int64)[None, :]
+        c = half + (b << rs)
+        classic = np.clip(oracle.right_shift(acc, rs) + b, -128, 127)       # RightShift (saturating), BiasAdd, Sp
+
+        def rha_plus_b(a):                                                  # (a + c + (a >> 31)) >> rs
+            return (a + c - (a < 0)) >> rs
+
+        folded = np.clip(rha_plus_b(np.clip(acc, a_lo, a_hi)), -128, 127)   # final clip == the saturating pack
+        assert np.array_equal(folded, classic), rs
+        relu = np.clip(np.maximum(rha_plus_b(np.minimum(acc, a_hi)), 0), -128, 127)
+        assert np.array_equal(relu, np.maximum(classic, 0)), rs
+        assert np.abs(np.clip(acc, a_lo, a_hi) + c).max() < 2 ** 31
