@@ -85,7 +85,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.first = gpu_index, [], None, 0
 
     def start(self):
         try:
@@ -101,13 +101,22 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self, wait_s=3.0):
+        """Call right before the timed region: waits until nvidia-smi has delivered its first sample (its NVML
+        start-up takes driver locks for ~50 ms and must not land inside the timed region) and discards what
+        was sampled so far."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < wait_s:
+            time.sleep(0.02)
+        self.first = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.thread.join(timeout=2)
         sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
+        for r in self.rows[self.first:] or self.rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
             except (ValueError, IndexError):
@@ -226,13 +235,15 @@ def ours(args):
         torch.empty(want, dtype=torch.uint8, device="cuda")
 
     # ---- value: inputs resident in HBM ---------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                    # started early: see ClockSampler.mark
     dev_batches = [make_batch(rank + world * i, device="cuda") for i in range(K)]
     prof = {}
     _native.set_profile(prof)
     l0 = _native.LAUNCHES["total"]
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     secs, q = run_job(net, ShardedBatches(dev_batches, K * world, rank, world), K * world, workdir, rank, world)
     clocks = sampler.stop() if rank == 0 else None
     launches = _native.LAUNCHES["total"] - l0
