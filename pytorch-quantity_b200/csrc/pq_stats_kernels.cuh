@@ -342,6 +342,20 @@ __device__ __forceinline__ void hist_redo_vecs(unsigned int redo, unsigned int *
     }
 }
 
+// rare path: does any flagged float4 of this thread hold an exact zero?  (re-loads them: nothing stays live
+// across the hot loop)
+__device__ __forceinline__ bool hist_flagged_has_zero(unsigned int redo, const float4 *psrc)
+{
+    bool z = false;
+    while (redo) {
+        const int slot = __ffs(redo) - 1;
+        redo &= redo - 1;
+        const float4 w = psrc[threadIdx.x + slot * kStatThreads];
+        z = z || w.x == 0.0f || w.y == 0.0f || w.z == 0.0f || w.w == 0.0f;
+    }
+    return z;
+}
+
 constexpr size_t hist_smem_bytes(int copies) { return 8192 + (size_t)copies * PQ_HIST_BINS * 4 + 128; }
 
 template <int COPIES, int VPT = kVecPerThread>
@@ -389,9 +403,13 @@ hist_multi_kernel(const __grid_constant__ SegTable tab, unsigned long long *__re
                         hist_redo_vecs<true>(redo, mine, mine_addr, psrc, hd);
                     } else {
                         const unsigned int redo = hist_add_vecs<false, VPT>(mine_addr, trash_addr, v, hd);
-                        // a warp that keeps flagging (exact zeros in the data) switches, for the rest
-                        // of its chunk range, to the variant that does not flag zeros
-                        zero_aware = __any_sync(0xffffffffu, __popc(redo) >= 3);
+                        // a warp that keeps flagging BECAUSE OF exact zeros switches, for the rest of its
+                        // chunk range, to the variant that does not flag zeros; flags raised by small
+                        // non-zero values (heavy-tailed data: everything in the lowest bins) do not count,
+                        // the zero-aware variant would only be slower on them
+                        bool many_zeros = false;
+                        if (__popc(redo) >= 3) many_zeros = hist_flagged_has_zero(redo, psrc);
+                        zero_aware = __any_sync(0xffffffffu, many_zeros);
                         hist_redo_vecs<false>(redo, mine, mine_addr, psrc, hd);
                     }
                 }
