@@ -280,7 +280,7 @@ def _read_workdir(test_dir):
 
 
 def _run_reference_pipeline(build_model, batches, input_shape, eval_batch, tag, worker_num=4,
-                            keep_feats=True, do_recon=True):
+                            keep_feats=True, do_recon=True, dkl_weight=False):
     import torch
     with ref_loader.reference_tools(input_shape, max_cali=len(batches) - 1,
                                     worker_num=worker_num,
@@ -316,6 +316,7 @@ def _run_reference_pipeline(build_model, batches, input_shape, eval_batch, tag, 
                 q.activation_quantize(batches)
                 t_act = time.time() - t0
                 t0 = time.time()
+                q._DKL_weight = bool(dkl_weight)        # pytorch_quantizer.py:62, :644-648
                 q.weight_quantize()
                 t_w = time.time() - t0
                 snap1 = _read_workdir(test_dir)
@@ -391,6 +392,19 @@ def gen_tiny():
     _save("tiny_e2e.npz", **arrays)
 
 
+def gen_tiny_dkl():
+    """The tiny net with the reference's KL mode for WEIGHTS switched on (``_DKL_weight``,
+    pytorch_quantizer.py:62, :644-648): weight bits from histogram + KL search instead of max-abs."""
+    ref_loader.install_shims()
+    sys.path.insert(0, ref_loader.REF_QUANTITY)
+    import tiny_fabu_net as tn
+    batches = tn.tiny_batches(3, 2, seed=1)
+    res, _arrays = _run_reference_pipeline(lambda: tn.build_tiny(0), batches, (1, 3, 16, 16), None, "tiny_dkl",
+                                           worker_num=2, keep_feats=False, do_recon=False, dkl_weight=True)
+    keep = {k: res[k] for k in ("after_weight_quantize", "after_second_rewrite")}
+    _save("tiny_dkl.npz", json=np.frombuffer(json.dumps(keep).encode(), dtype=np.uint8))
+
+
 def gen_lenet():
     """The reference's LeNet example (quantity/test/lenet_quantity.py + lenet_reconstruction.py) on synthetic
     MNIST-shaped inputs: single input channel, 5x5 kernel, three stacked Linear layers, no BatchNorm."""
@@ -452,7 +466,7 @@ def gen_r18_224():
 
 
 SECTIONS = {"stats": gen_stats, "kl": gen_kl, "fakequant": gen_fakequant, "intsim": gen_intsim,
-            "tiny": gen_tiny, "lenet": gen_lenet, "r18_224": gen_r18_224}
+            "tiny": gen_tiny, "tiny_dkl": gen_tiny_dkl, "lenet": gen_lenet, "r18_224": gen_r18_224}
 
 if __name__ == "__main__":
     assert ref_loader.available(), "needs /root/reference"

@@ -159,3 +159,28 @@ def test_tiny_recontest_outputs(tmp_path):
     assert np.abs(outs["conv0.0"] - ref0).max() <= step
     assert (outs["conv0.0"] != ref0).mean() < 1e-3
     assert np.abs(y - g["ReconTest/y"]).max() <= 4 * 2.0 ** -info["fc"]["output_bit"]
+
+
+def test_tiny_dkl_weight_mode(tmp_path):
+    """The reference's KL mode for weights (``_DKL_weight``, pytorch_quantizer.py:62, :644-648): weight histograms
+    and the KL search on the GPU give the reference's weight.table and weight / bias JSON."""
+    import hashlib
+    import common.quantity as cq
+    import tools
+    g = load_golden("tiny_e2e.npz")
+    j = golden_json(load_golden("tiny_dkl.npz"))
+    cfg, user = _configs(tmp_path, (1, 3, 16, 16), 2)
+    with torch.no_grad():
+        q = tools.Quantity(cq.merge_bn(_tiny_model(g), "cpu"), config=cfg, user_config=user, verbose=False)
+        q.activation_quantize([(torch.from_numpy(g["batch%d" % i]), None) for i in range(3)])
+        q._DKL_weight = True
+        q.weight_quantize()
+        snap1 = _snapshot(cfg)
+        q.rewrite_weight()
+        snap2 = _snapshot(cfg)
+    for snap, key in ((snap1, "after_weight_quantize"), (snap2, "after_second_rewrite")):
+        ref = j[key]
+        assert snap["weight.table"] == ref["weight.table"], key
+        for name, val in ref.items():
+            if isinstance(val, dict):
+                assert hashlib.md5(snap[name]).hexdigest() == val["md5"], (key, name)
