@@ -266,14 +266,19 @@ def merge_bn_params(weight, bias, gamma, beta, mean, var):
 
 
 # ---------------------------------------------------------------------- a8 / a9
-def weight_quantize(params):
-    """tools/pytorch_quantizer.py:635-669 with _DKL_weight=False.
+def weight_quantize(params, dkl=False):
+    """tools/pytorch_quantizer.py:635-669.  dkl=False: bit from max-abs (:650-653, the shipped setting
+    ``_DKL_weight = False``, :62); dkl=True: histogram + KL search per parameter (:644-648).
     params: ordered dict name -> float32 ndarray.  Returns (bits, q_int32 arrays)."""
     bits, q = {}, {}
     for name, p in params.items():
         p32 = np.asarray(p, dtype=np.float32)
         m = absmax_update(0, p32)
-        bit = maxabs_to_bit(m)
+        if dkl:
+            interv = interval(m)
+            bit = quantize_distribution(hist(p32, interv), interv)[0]
+        else:
+            bit = maxabs_to_bit(m)
         v = np.clip(np.around(p32.reshape(-1) * math.pow(2, bit)), -128, 127)
         bits[name] = bit
         q[name] = v.reshape(p32.shape).astype(np.int32)

@@ -151,10 +151,12 @@ def test_tiny_calibration_tables(oracle):
     assert "\n".join(lines) + "\n" == j["after_weight_quantize"]["feat.table"]
 
 
-def test_tiny_weight_quantize_and_rewrite(oracle):
+@pytest.mark.parametrize("dkl", [False, True], ids=["maxabs", "dkl"])
+def test_tiny_weight_quantize_and_rewrite(oracle, dkl):
+    """dkl: the reference's KL mode for weights (``_DKL_weight``, pytorch_quantizer.py:644-648; golden tiny_dkl.npz)."""
     import torch
     g = load_golden("tiny_e2e.npz")
-    j = golden_json(g)
+    j = golden_json(load_golden("tiny_dkl.npz")) if dkl else golden_json(g)
     # merged-BN parameters, in named_parameters order of the merged model
     import tiny_fabu_net as tn
     net = tn.build_tiny(0)
@@ -172,7 +174,7 @@ def test_tiny_weight_quantize_and_rewrite(oracle):
                                           m.weight.data, m.bias.data, m.running_mean, m.running_var)
             params[cname + ".weight"], params[cname + ".bias"] = w, b
     params["fc.weight"], params["fc.bias"] = mods["fc"].weight.data.numpy(), mods["fc"].bias.data.numpy()
-    bits, q = oracle.weight_quantize(params)
+    bits, q = oracle.weight_quantize(params, dkl=dkl)
     snap = j["after_weight_quantize"]
     for name in params:
         sub = "weight/" if name.endswith("weight") else "bias/"
