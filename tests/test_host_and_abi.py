@@ -126,3 +126,75 @@ def test_graph_pruning_and_merge_groups_host_logic():
     pruned = q.prune_net_info(full, keep)
     assert pruned == j["net_info"] and list(pruned) == list(j["net_info"])
     assert q.get_merge_groups(pruned) == j["merge_groups"]
+
+
+# Public surface of the reference's common.quantity package (quantity/common/quantity/__init__.py:1-6), recorded by
+# inspecting the unmodified reference: constructor / function parameters (name, default) and forward() parameters.
+_REQ = object()
+REFERENCE_SURFACE = {
+    "DistributionCollector": ([("tensor_list", _REQ), ("interval_num", 2048), ("statistic", 1), ("worker_num", 1),
+                               ("debug", False)], None,
+                              ["add_to_distributions", "distribution_intervals", "distributions", "max_vals", "refresh_max_val"]),
+    "Quantizer": ([("tensor_list", _REQ), ("worker_num", 1), ("debug", False)], None,
+                  ["bits", "quantize", "threshold_value"]),
+    "BitReader": ([("feat_table", None), ("weight_table", None)], None, ["get_feat_info", "get_weight_info"]),
+    "merge_bn": ([("model", _REQ), ("device", "cpu")], None, []),
+    "walk_dirs": ([("dir_name", _REQ), ("file_type", None)], None, []),
+    "tid": ([("tensor", _REQ)], None, []),
+    "Eltwise": ([], ["x", "y"], []), "Concat": ([], ["x", "y", "dim"], []), "Identity": ([], ["x"], []),
+    "View": ([], ["x"], []),
+    "RightShift": ([("bits", _REQ), ("rs", _REQ)], ["x"], []), "Sp": ([("bits", _REQ)], ["x"], []),
+    "BiasAdd": ([], ["x", "y"], []),
+    "NewConv2d": ([("conv_module", _REQ), ("quantize_infor", _REQ)], ["input"], ["quantity"]),
+    "NewAdd": ([], ["x", "y"], []),
+    "NewLinear": ([("linear_module", _REQ), ("quantize_infor", _REQ)], ["input"], ["quantity"]),
+    "QuanDequan": ([("Bitwidth", _REQ), ("bit", _REQ)], ["quantized_x"], []),
+    "TestConv": ([("name", _REQ), ("module", _REQ), ("quantize_infor", _REQ), ("new_model_path", _REQ)], ["x"], []),
+    "TestLinear": ([("name", _REQ), ("module", _REQ), ("quantize_infor", _REQ), ("new_model_path", _REQ)], ["x"], []),
+    "Quantity": ([("ib", _REQ)], ["x"], []), "DeQuantity": ([("ob", _REQ)], ["x"], []),
+}
+
+
+def test_public_surface_matches_the_reference():
+    """Same 21 names, same leading constructor / function parameters (names and defaults; extra trailing keyword
+    parameters such as ``device`` are allowed), same forward() parameter names, same public members."""
+    import inspect
+    import common.quantity as cq
+    assert sorted(cq.__all__) == sorted(REFERENCE_SURFACE)
+    for name, (params, fwd, members) in REFERENCE_SURFACE.items():
+        obj = getattr(cq, name)
+        sig = inspect.signature(obj.__init__ if inspect.isclass(obj) else obj)
+        got = [p for p in sig.parameters.values() if p.name != "self" and p.kind in (p.POSITIONAL_OR_KEYWORD,)]
+        assert len(got) >= len(params), name
+        for have, (pname, default) in zip(got, params):
+            assert have.name == pname, (name, have.name, pname)
+            if default is _REQ:
+                assert have.default is inspect.Parameter.empty, (name, pname)
+            else:
+                assert have.default == default, (name, pname)
+        for extra in got[len(params):]:
+            assert extra.default is not inspect.Parameter.empty, (name, extra.name)   # extensions must be optional
+        if fwd is not None:
+            fparams = [p for p in inspect.signature(obj.forward).parameters if p != "self"]
+            assert fparams[:len(fwd)] == fwd, (name, fparams)
+        for m in members:
+            assert hasattr(obj, m), (name, m)
+
+
+def test_tools_surface_matches_the_reference():
+    """quantity/tools/__init__.py:1-3 exports Quantity, Reconstruction, BiasReWriter with these entry points."""
+    import inspect
+    import tools
+    for cls, methods in (("Quantity", ["activation_quantize", "weight_quantize", "rewrite_weight", "build_net_structure",
+                                       "get_merge_groups", "preprocess", "dilation_to_zero_padding", "init_dir"]),
+                         ("Reconstruction", ["merge_bn", "get_quantity_information", "ReconModel", "ReconTest"]),
+                         ("BiasReWriter", ["get_weight_info", "get_feat_info", "rewrite_bias_table", "rewrite_bias_dir",
+                                           "max_shift_limit_weight", "rewrite_weight_table", "rewrite_weight_dir"])):
+        obj = getattr(tools, cls)
+        for m in methods:
+            assert callable(getattr(obj, m)), (cls, m)
+    assert list(inspect.signature(tools.Quantity.__init__).parameters)[:2] == ["self", "model"]
+    assert list(inspect.signature(tools.Reconstruction.__init__).parameters)[:2] == ["self", "model"]
+    for m in ("ReconModel", "ReconTest"):               # reconstruction.py:175, :243
+        assert list(inspect.signature(getattr(tools.Reconstruction, m)).parameters) == \
+            ["self", "all_quantize_infor", "new_model_path"], m
