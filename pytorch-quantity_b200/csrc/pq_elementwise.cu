@@ -258,6 +258,45 @@ quantize_im2col_kernel(const float *__restrict__ x, int8_t *__restrict__ a, int 
 // zero-padded NHWC image with 8-byte pixels, q[n][h + ph][w + pw][c] = q(x[n][c][h][w]); everything else
 // (spatial padding, channel slots c >= C) is written as 0.  One thread per padded pixel: C coalesced fp32
 // loads along w, one coalesced 8-byte store.
+// Variant for C <= 4 (RGB inputs): two padded rows per thread, every load of both rows issued before the first
+// conversion (12 loads in flight for C = 3) and half as many, longer-lived blocks; the channel loop is a
+// compile-time 4, so the values stay in 16 registers (a 4-row / 8-channel version needed 94 and was slower).
+__global__ void __launch_bounds__(128)
+quantize_pad_nhwc8_c4_kernel(const float *__restrict__ x, uint2 *__restrict__ q, int C, int H, int W, int ph, int pw,
+                             int Hp, int Wp, float scale)
+{
+    const int wp = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (wp >= Wp) return;
+    const size_t n = blockIdx.z;
+    const size_t HW = (size_t)H * W;
+    const int hp0 = blockIdx.y * 2;
+    float v[2][2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int h = hp0 + r - ph;
+        const float *row = x + (n * C * H + (size_t)(h < 0 ? 0 : h)) * (size_t)W;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int w = wp + k - pw;
+            const bool ok = (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[r][k][c] = (ok && c < C) ? __ldg(row + c * HW + w) : 0.0f;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int hp = hp0 + r;
+        if (hp >= Hp) break;
+        unsigned int word[2] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < C) word[k] |= ((unsigned int)q8i(v[r][k][c], scale) & 0xffu) << (c * 8);
+        *reinterpret_cast<uint4 *>(q + (n * Hp + hp) * (size_t)Wp + wp) = make_uint4(word[0], 0u, word[1], 0u);
+    }
+}
+
 __global__ void __launch_bounds__(kEwThreads)
 quantize_pad_nhwc8_kernel(const float *__restrict__ x, uint2 *__restrict__ q, int C, int H, int W, int ph, int pw,
                           int Hp, int Wp, float scale)
@@ -403,6 +442,12 @@ extern "C" int pq_quantize_nchw_to_padded_nhwc8_s8(const float *x, int8_t *q, in
     if (Hp > 65535 || N > 65535) return PQ_EUNSUPPORTED;
     const int threads = Wp / 2 <= 128 ? 128 : pq::kEwThreads;          // a 224-wide image is 115 pixel pairs per row
     const dim3 grid((unsigned)((Wp / 2 + threads - 1) / threads), (unsigned)Hp, (unsigned)N);
+    if (C <= 4) {
+        const dim3 grid2((unsigned)((Wp / 2 + 127) / 128), (unsigned)((Hp + 1) / 2), (unsigned)N);
+        pq::quantize_pad_nhwc8_c4_kernel<<<grid2, 128, 0, (cudaStream_t)stream>>>(
+            x, reinterpret_cast<uint2 *>(q), C, H, W, pad_h, pad_w, Hp, Wp, ldexpf(1.0f, ib));
+        return (int)cudaGetLastError();
+    }
     pq::quantize_pad_nhwc8_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
         x, reinterpret_cast<uint2 *>(q), C, H, W, pad_h, pad_w, Hp, Wp, ldexpf(1.0f, ib));
     return (int)cudaGetLastError();
