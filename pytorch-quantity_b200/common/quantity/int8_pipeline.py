@@ -28,7 +28,7 @@ from . import _native
 
 # NewConv2d + NewAdd (+ ReLU) in one kernel (pq_conv2d_s8_add).  Bit-identical, but on B200 the fused
 # epilogue is instruction-bound and currently slower than the HBM-bound pq_add_requant_ex it replaces
-# (ResNet-50 batch 512: 5.5 ms vs 1.3 + 2.8 ms), so it is off by default; see DESIGN.md section 4.
+# (ResNet-50 batch 512: 5.5 ms vs 1.3 + 2.5 ms), so it is off by default; see DESIGN.md section 4.
 FUSE_ADD_INTO_CONV = False
 
 _METADATA = {"__get__", "size", "dim", "numel", "element_size", "ndimension", "is_floating_point", "__len__",
