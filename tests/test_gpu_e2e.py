@@ -184,3 +184,52 @@ def test_tiny_dkl_weight_mode(tmp_path):
         for name, val in ref.items():
             if isinstance(val, dict):
                 assert hashlib.md5(snap[name]).hexdigest() == val["md5"], (key, name)
+
+
+def test_c1_resnet18_kl_search_on_reference_histograms():
+    """BASELINE config 1: the reference's merged histograms of its full ResNet-18 224x224 CPU run (30 tensors) ->
+    the GPU KL search + host bit derivation give the reference's thresholds and raw bits exactly."""
+    import common.quantity as cq
+    g = load_golden("r18_224_c1.npz")
+    j = golden_json(g)
+    names = [k[len("dist/"):] for k in g.files if k.startswith("dist/")]
+    qz = cq.Quantizer(names)
+    qz.quantize({n: g["dist/" + n] for n in names}, {n: np.float32(j["intervals"][n]) for n in names})
+    assert qz.bits == {n: j["raw_bits"][n] for n in names}
+    for n in names:
+        assert float(qz.threshold_value[n]) == j["thresholds"][n], n
+
+
+def test_c1_resnet18_calibration_vs_reference_run(tmp_path):
+    """BASELINE config 1 end to end on the GPU: same seeded ResNet-18, same 8 batches of 8 synthetic 224x224 images
+    as the reference's CPU run.  Tracer output and the int8 weight JSON are identical; the activation statistics come
+    from a cuDNN forward instead of MKLDNN, so a fractional bit may move by one where a threshold sits on the edge."""
+    import hashlib
+    import sys
+    import common.quantity as cq
+    import tools
+    from model.resnet.resnet_fabu import randomize_bn_, resnet18_fabu
+    j = golden_json(load_golden("r18_224_c1.npz"))
+    torch.manual_seed(0)
+    net = resnet18_fabu().eval()
+    with torch.no_grad():
+        randomize_bn_(net, 0)
+    batches = [(torch.randn(8, 3, 224, 224, generator=torch.Generator().manual_seed(1 + i)), None) for i in range(8)]
+    cfg, user = _configs(tmp_path, (1, 3, 224, 224), 7)
+    with torch.no_grad():
+        q = tools.Quantity(cq.merge_bn(net, "cpu"), config=cfg, user_config=user, verbose=False)
+        assert dict(q.net_info) == j["net_info"] and q.cared_op_layer_names == j["cared_op_layer_names"]
+        assert q.get_merge_groups(q.net_info) == j["merge_groups"]
+        q.activation_quantize(batches)
+        q.weight_quantize()
+    snap = _snapshot(cfg)
+    ref = j["after_weight_quantize"]
+    got_lines, ref_lines = snap["feat.table"].strip().split("\n"), ref["feat.table"].strip().split("\n")
+    assert [l.split()[0] for l in got_lines] == [l.split()[0] for l in ref_lines]
+    diffs = [(a, b) for a, b in zip(got_lines, ref_lines) if a != b]
+    assert len(diffs) <= 3, diffs
+    for a, b in diffs:
+        assert max(abs(int(x) - int(y)) for x, y in zip(a.split()[1:], b.split()[1:])) <= 1, (a, b)
+    for name, val in ref.items():
+        if name.startswith("weight/"):                       # int8 weights: independent of the activation tables
+            assert hashlib.md5(snap[name]).hexdigest() == val["md5"], name

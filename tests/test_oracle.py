@@ -354,3 +354,18 @@ def test_folded_bias_identity(oracle):
         relu = np.clip(np.maximum(rha_plus_b(np.minimum(acc, a_hi)), 0), -128, 127)
         assert np.array_equal(relu, np.maximum(classic, 0)), rs
         assert np.abs(np.clip(acc, a_lo, a_hi) + c).max() < 2 ** 31
+
+
+def test_c1_resnet18_reference_histograms(oracle):
+    """BASELINE config 1 (ResNet-18 224x224, 64 images, the reference's full CPU run): from the reference's own
+    merged histograms and intervals, the oracle's KL search + bit derivation reproduce every threshold and raw bit."""
+    g = load_golden("r18_224_c1.npz")
+    j = golden_json(g)
+    names = [k[len("dist/"):] for k in g.files if k.startswith("dist/")]
+    assert len(names) == 30 and "image" in names
+    assert int(g["dist/image"].sum()) == 64 * 3 * 224 * 224            # every (non-zero) input element counted once
+    for n in names:
+        interv = np.float32(j["intervals"][n])
+        bit, thr, _t = oracle.quantize_distribution(g["dist/" + n], interv)
+        assert float(thr) == j["thresholds"][n], n
+        assert bit == j["raw_bits"][n], n
