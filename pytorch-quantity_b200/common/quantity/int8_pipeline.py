@@ -36,20 +36,24 @@ _METADATA = {"__get__", "size", "dim", "numel", "element_size", "ndimension", "i
 
 
 class _LazyConv:
-    """A NewConv2d whose kernel has not run yet.  If its only consumer turns out to be a NewAdd, the add
-    (and the ReLU after it) run inside the conv's epilogue and the conv result never touches memory."""
+    """A NewConv2d whose kernel has not run yet.  It runs when the first consumer asks for the int8 payload, by
+    which time it is known whether an nn.ReLU was applied in between: that ReLU is then fused into the conv
+    epilogue.  The decision is taken per request, not from module adjacency, so whoever observes the conv's OWN
+    output (a forward hook on the NewConv2d, ``seq[0](x)`` on its own, a sliced Sequential) still gets pre-ReLU
+    values, exactly like the fp32-boundary model.  If the only consumer is a NewAdd, the add (and the ReLU after
+    it) can run inside the conv's epilogue and the conv result never touches memory."""
 
-    def __init__(self, mod, q):
-        self.mod, self.q, self.out = mod, q, None
+    def __init__(self, mod, run, q=None):
+        self.mod, self.run, self.q = mod, run, q       # q: int8 NHWC operand (kept for the fused conv+add kernel)
+        self.out = {}                                  # relu -> int8 NHWC payload
 
-    def get(self):
-        if self.out is None:
-            mod, conv = self.mod, self.mod.Conv
-            _, self.out = _native.conv2d_s8(self.q, mod._w_krsc, mod._bias_i32, conv.stride, conv.padding, mod.rs_bit,
-                                            mod.output_bit, want_f32=False, want_s8=True, c_real=conv.in_channels,
-                                            relu=mod._fuse_relu)
-            self.q = None
-        return self.out
+    def get(self, relu):
+        if relu not in self.out:
+            if relu and False in self.out:             # both asked for (rare): ReLU of the payload already there
+                self.out[True] = _native.relu_s8(self.out[False])
+            else:
+                self.out[relu] = self.run(relu)
+        return self.out[relu]
 
 
 class _LazyAdd:
@@ -72,7 +76,7 @@ class _LazyAdd:
     @staticmethod
     def _fusable(t):
         lc = t._lazy_conv
-        return FUSE_ADD_INTO_CONV and lc is not None and lc.out is None and not t.relu_pending and not lc.mod._fuse_relu \
+        return FUSE_ADD_INTO_CONV and lc is not None and lc.q is not None and not lc.out and not t.relu_pending \
             and lc.mod.Conv.out_channels % 16 == 0
 
     def get(self, relu, kind):
@@ -170,8 +174,11 @@ class QTensor(torch.Tensor):
 
     def _materialize(self, kind):
         if self._lazy_conv is not None:
-            self._q8 = self._lazy_conv.get()
+            relu = self.relu_pending
+            self._q8 = self._lazy_conv.get(relu)       # a pending ReLU is applied by the conv epilogue
             self._lazy_conv = None
+            self._q8_relu = None
+            self.nonneg = self.nonneg or relu
         if self._lazy is not None and (self._s16 if kind == "s16" else self._q8) is None:
             relu = self.relu_pending
             have = self._lazy.get(relu, kind)           # the pending ReLU is applied by the add kernel
@@ -324,25 +331,38 @@ def conv_forward(mod, x):
     elif isinstance(x, QTensor):
         q = x.int8_payload()                                     # Quantity(ib) is the identity here
     elif getattr(mod, "_smallc", False):
-        _, out8 = mod._smallc_forward(x, want_f32=False, want_s8=True, relu=mod._fuse_relu)
-        N, P, Q, K = out8.shape
-        return QTensor((N, K, P, Q), out8.device, q8=out8, q8_bit=mod.output_bit, nonneg=mod._fuse_relu)
+        N, _, H, W = x.shape
+        (R, S), (sh, sw), (ph, pw) = conv.kernel_size, conv.stride, conv.padding
+        P, Q = (H + 2 * ph - R) // sh + 1, (W + 2 * pw - S) // sw + 1
+
+        def run_smallc(relu, x=x):
+            return mod._smallc_forward(x, want_f32=False, want_s8=True, relu=relu)[1]
+        return QTensor((N, conv.out_channels, P, Q), x.device, q8_bit=mod.output_bit,
+                       lazy_conv=_LazyConv(mod, run_smallc))
     elif mod._explicit_im2col:
         a, (N, P, Q) = _native.quantize_im2col_s8(x, mod.input_bit, conv.kernel_size, conv.stride,
                                                   conv.padding, mod._k_pad)
-        _, out8 = _native.gemm_s8(a, mod._w_nk, mod._bias_i32, mod.rs_bit, mod.output_bit, hw=1,
-                                  want_f32=False, want_s8=True, relu=mod._fuse_relu,
-                                  k_real=conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1])
-        return QTensor((N, conv.out_channels, P, Q), out8.device, q8=out8.view(N, P, Q, conv.out_channels),
-                       q8_bit=mod.output_bit, nonneg=mod._fuse_relu)
+
+        def run_gemm(relu, a=a):
+            _, out8 = _native.gemm_s8(a, mod._w_nk, mod._bias_i32, mod.rs_bit, mod.output_bit, hw=1,
+                                      want_f32=False, want_s8=True, relu=relu,
+                                      k_real=conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1])
+            return out8.view(N, P, Q, conv.out_channels)
+        return QTensor((N, conv.out_channels, P, Q), a.device, q8_bit=mod.output_bit,
+                       lazy_conv=_LazyConv(mod, run_gemm))
     else:
         q = _native.quantize_nchw_to_nhwc_s8(x, mod.input_bit, mod._c_pad)
     N, H, W, _ = q.shape
     (R, S), (sh, sw), (ph, pw) = conv.kernel_size, conv.stride, conv.padding
     P, Q = (H + 2 * ph - R) // sh + 1, (W + 2 * pw - S) // sw + 1
-    # deferred: a NewAdd consumer can absorb this convolution into one fused kernel
-    return QTensor((N, conv.out_channels, P, Q), q.device, q8_bit=mod.output_bit, nonneg=mod._fuse_relu,
-                   lazy_conv=_LazyConv(mod, q))
+
+    def run_conv(relu, q=q):
+        return _native.conv2d_s8(q, mod._w_krsc, mod._bias_i32, conv.stride, conv.padding, mod.rs_bit,
+                                 mod.output_bit, want_f32=False, want_s8=True, c_real=conv.in_channels,
+                                 relu=relu)[1]
+    # deferred: the ReLU that may follow is fused on demand, and a NewAdd consumer can absorb the whole convolution
+    return QTensor((N, conv.out_channels, P, Q), q.device, q8_bit=mod.output_bit,
+                   lazy_conv=_LazyConv(mod, run_conv, q))
 
 
 def _operand(t):
@@ -371,28 +391,15 @@ def add_forward(mod, x, y):
 
 
 def enable_int8_pipeline(model, enabled=True):
-    """Switch a ReconModel to the int8 inter-layer pipeline (or back).  Also marks every NewConv2d that
-    is directly followed by an nn.ReLU inside an nn.Sequential (Identity modules in between are
-    skipped) so that its epilogue applies the ReLU."""
-    from .fabu_layer import Identity
+    """Switch a ReconModel to the int8 inter-layer pipeline (or back).  Nothing is decided from module adjacency:
+    a ReLU after a convolution is fused into its epilogue when the (lazy) convolution finally runs for a consumer
+    that sits behind that ReLU (see _LazyConv)."""
     from .new_quantity_op import NewAdd, NewConv2d
     for m in model.modules():
         if isinstance(m, (NewConv2d, NewAdd)):
             m.int8_pipeline = enabled
         if isinstance(m, NewConv2d):
-            m._fuse_relu = False
-    if enabled:
-        for seq in model.modules():
-            if not isinstance(seq, nn.Sequential):
-                continue
-            kids = list(seq.children())
-            for i, k in enumerate(kids):
-                if isinstance(k, NewConv2d):
-                    j = i + 1
-                    while j < len(kids) and isinstance(kids[j], Identity):
-                        j += 1
-                    if j < len(kids) and isinstance(kids[j], nn.ReLU):
-                        k._fuse_relu = True
+            m._fuse_relu = False                       # kept for models pickled by earlier versions; unused
     return model
 
 

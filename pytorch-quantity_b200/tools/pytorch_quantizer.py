@@ -40,6 +40,13 @@ def _dist_info():
     return 0, 1
 
 
+def _barrier():
+    """Rank 0 alone writes the tables / JSON; the other ranks must not run ahead and read partial files."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
 class Quantity(object):
 
     def __init__(self, model, config=None, user_config=None, cache_bytes=None, verbose=True):
@@ -64,11 +71,19 @@ class Quantity(object):
         self._merge_op_type = settings["MERGE_OP_YTPE"]
         self._max_img_num = settings["MAX_CALI_IMG_NUM"]
         self._log("max_img_num", self._max_img_num)
-        self.model = model.to(self.cuda_device).eval()
+        # The reference leaves the caller's model alone (:57); here it must live on the GPU (no CPU fallback), but
+        # its train/eval mode is the caller's business exactly as in the reference.
+        self.model = model.to(self.cuda_device)
+        if self.model.training:
+            import warnings
+            warnings.warn("Quantity: the model is in training mode (Dropout / un-merged BatchNorm would perturb the "
+                          "statistics); the reference does not switch modes either -- call model.eval() first")
         self.input_size = tuple(int(v) for v in str(self.user_config["MODEL"]["INPUT_SHAPE"]).split(","))
         self.layers_num = 0
         self.name_to_param = OrderedDict()
         self.cache_bytes = cache_bytes
+        self._begin_forward = lambda: None
+        self._inplace_modified = set()
         self.net_info = self.build_net_structure(self.model, self.input_size, self.device)
         self.cared_op_layer_names = self.get_cared_op_names(self.model)
         self._DKL_weight = False
@@ -90,6 +105,7 @@ class Quantity(object):
         keep_alive = []             # tensors stay referenced so ids cannot be recycled
         hooks = []
         orphan = []
+        observed = []               # (tracer name, tensor, version at hook time): what calibration will record
 
         def _hook(m, inputs, output):
             kind = type(m).__name__
@@ -106,9 +122,13 @@ class Quantity(object):
                     orphan.append(name)       # only the first layer may read the network input
             if any(t is output for t in inputs if isinstance(t, torch.Tensor)) and kind not in allow_same:
                 raise ValueError("Same input and output id, the op {} is useful?".format(name))
+            if not net and inputs and isinstance(inputs[0], torch.Tensor):
+                observed.append(("image", inputs[0], inputs[0]._version))
             net[name] = {"inputs": srcs, "type": kind}
             producer_of[id(output)] = name    # in-place / pass-through ops take over the tensor
             keep_alive.append((inputs, output))
+            if isinstance(output, torch.Tensor):
+                observed.append((name, output, output._version))
 
         for m in model.modules():
             if type(m).__name__ in all_op_type:
@@ -120,6 +140,11 @@ class Quantity(object):
             h.remove()
         assert not orphan, "Can't find the input tensor of {} \n {}".format(orphan[0], net)
         self.layers_num = len(net)
+        # Tensors a later in-place op (nn.ReLU(inplace=True), ``out += residual``) overwrites after their hook
+        # fired.  The reference snapshots every hooked output to numpy at hook time (:509,:513), so it records the
+        # pre-modification values; the calibration hooks below keep device references and therefore clone
+        # exactly these tensors (and only these) to record the same values.
+        self._inplace_modified = {n for n, t, v in observed if t._version != v}
         keep = [n for n, info in net.items() if info["type"] in self._cared_op_type]
         return self.prune_net_info(net, keep)
 
@@ -250,24 +275,48 @@ class Quantity(object):
         hooks = []
         cared = self._cared_op_type
         state = {"idx": 0}
+        versions = {}
+        clone = self._inplace_modified
+        self._feat_versions = versions
 
         def _begin():
             state["idx"] = 0
             out_feat.clear()
+            versions.clear()
+
+        def _keep(name, t):
+            t = t.detach()
+            if name in clone:
+                t = t.clone()              # a later in-place op overwrites it (found by build_net_structure)
+            out_feat[name] = t
+            versions[name] = t._version
 
         def _hook(m, inputs, output):
+            if state["idx"] >= self.layers_num:
+                _begin()                   # a new forward started without _begin_forward (plain ``model(x)``, :497-500)
             if state["idx"] == 0:
-                out_feat["image"] = inputs[0].detach()
+                _keep("image", inputs[0])
             state["idx"] += 1
             kind = type(m).__name__
             if kind in cared:
-                out_feat["%s_%i" % (kind, state["idx"])] = output.detach()
+                _keep("%s_%i" % (kind, state["idx"]), output)
 
         for m in model.modules():
             if type(m).__name__ in self._all_op_type:
                 hooks.append(m.register_forward_hook(_hook))
         self._begin_forward = _begin
         return out_feat, hooks
+
+    def _check_unmodified(self, feats):
+        """The observed tensors are device references, not the host snapshots of the reference (:509,:513): a
+        tensor modified in place after its hook fired would silently yield post-modification statistics."""
+        for name, t in feats.items():
+            v = self._feat_versions.get(name) if feats is self._named_feats_live else None
+            if v is not None and t._version != v:
+                raise RuntimeError(
+                    "calibration tensor %r was modified in place after it was observed (nn.ReLU(inplace=True), "
+                    "`out += residual`, ...) in a way the tracing forward did not show; the reference records "
+                    "the value at hook time. Use out-of-place ops for data-dependent control flow." % name)
 
     def _my_batches(self, images_files):
         """Batches 0..MAX_CALI_IMG_NUM (reference :381), round-robin over data-parallel ranks."""
@@ -290,6 +339,7 @@ class Quantity(object):
                                           worker_num=settings["WORKER_NUM"], device=self.cuda_device)
         quantizer = Quantizer(top_feat_names, worker_num=settings["WORKER_NUM"], device=self.cuda_device)
         named_feats, hooks = self.regist_hook_outfeature(self.model)
+        self._named_feats_live = named_feats
 
         # HBM activation cache for pass 2
         budget = self.cache_bytes
@@ -304,6 +354,7 @@ class Quantity(object):
         n_mine = 0
         for i, img in self._device_batches(images_files):                    # pass 1  (:379-390)
             self._forward_device(self.model, img)
+            self._check_unmodified(named_feats)
             feats = {n: named_feats[n] for n in top_feat_names}
             collector.refresh_max_val(feats)
             nbytes = sum(t.numel() * t.element_size() for t in feats.values())
@@ -338,6 +389,7 @@ class Quantity(object):
                 feats = cache.pop(i)
             else:
                 self._forward_device(self.model, img)
+                self._check_unmodified(named_feats)
                 feats = {n: named_feats[n] for n in top_feat_names}
             collector.add_to_distributions(feats)
         if n_mine == 0:
@@ -389,6 +441,7 @@ class Quantity(object):
             with open(table_file, "w") as f:
                 for line in lines:
                     f.write(line + "\n")
+        _barrier()
         self.timings.update(pass1_s=t1 - t0, pass2_s=t2 - t1, kl_s=t3 - t2,
                             batches=n_mine, cached_batches=n_cached, cached_bytes=cached_bytes)
         self.last_calibration = dict(bits=dict(bits), intervals=dict(distribution_intervals),
@@ -402,15 +455,18 @@ class Quantity(object):
     # -------------------------------------------------------------------------- files
     def init_dir(self):
         out = self.config["OUTPUT"]
-        if self.rank != 0:
-            return
-        for key in ("WORK_DIR", "WEIGHT_DIR", "BIAS_DIR", "FINAL_WEIGHT_DIR", "FINAL_BIAS_DIR"):
-            os.makedirs(out[key], exist_ok=True)
+        if self.rank == 0:
+            for key in ("WORK_DIR", "WEIGHT_DIR", "BIAS_DIR", "FINAL_WEIGHT_DIR", "FINAL_BIAS_DIR"):
+                os.makedirs(out[key], exist_ok=True)
+        _barrier()
 
     def rewrite_weight(self):
         """Align bias bits to the output bits and cap the shift (reference :553-590)."""
-        if self.rank != 0:
-            return
+        if self.rank == 0:
+            self._rewrite_weight_rank0()
+        _barrier()
+
+    def _rewrite_weight_rank0(self):
         out = self.config["OUTPUT"]
         rewriter = BiasReWriter(out["WEIGHT_DIR"], out["BIAS_DIR"], out["FINAL_WEIGHT_DIR"],
                                 out["FINAL_BIAS_DIR"], out["WEIGHT_BIT_TABLE"], out["FEAT_BIT_TABLE"],
@@ -486,6 +542,7 @@ class Quantity(object):
             with open(out["WEIGHT_BIT_TABLE"], "w") as f:
                 for line in table:
                     f.write(line + "\n")
+        _barrier()
         self.rewrite_weight()
 
     def dilation_to_zero_padding(self, tensor, dilation):

@@ -26,7 +26,14 @@ import tempfile
 import time
 import types
 
-REF_ROOT = os.environ.get("PQ_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    """/root/reference in the build container; the staged byte copy baseline/_ref (stage_ref.py) elsewhere."""
+    if os.path.isdir("/root/reference/quantity"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "baseline", "_ref")
+
+
+REF_ROOT = os.environ.get("PQ_REFERENCE_ROOT") or _default_root()
 REF_QUANTITY = os.path.join(REF_ROOT, "quantity")
 
 
@@ -140,18 +147,20 @@ def stage_workdir(input_shape, max_cali, worker_num=4, device="cpu", root=None):
 
 
 @contextlib.contextmanager
-def reference_tools(input_shape, max_cali, worker_num=4, extra_sys_path=()):
+def reference_tools(input_shape, max_cali, worker_num=4, extra_sys_path=(), device="cpu", foreign_common=False):
     """Context: cwd = staged test dir, sys.path[0] = reference quantity/, yields the
     reference ``tools`` package.  Must not be used in a process that already
     imported this repo's ``common``/``tools`` (same top-level names by design)."""
     install_shims()
     for k in list(sys.modules):
+        if foreign_common and (k == "common" or k.startswith("common.")):
+            continue            # boundary proof: the reference's tools/ on top of the drop-in common.quantity
         if k == "common" or k.startswith("common.") or k == "tools" or k.startswith("tools."):
             f = getattr(sys.modules[k], "__file__", "") or ""
             assert f.startswith(REF_ROOT) or not f, (
                 "this process already imported a non-reference '%s' (%s)" % (k, f))
     cwd0 = os.getcwd()
-    test_dir = stage_workdir(input_shape, max_cali, worker_num)
+    test_dir = stage_workdir(input_shape, max_cali, worker_num, device=device)
     paths = [REF_QUANTITY] + list(extra_sys_path)
     for p in reversed(paths):
         sys.path.insert(0, p)
