@@ -18,8 +18,14 @@ rank; value = N*K*64 images / max-over-ranks device time.  Weak scaling: per-ran
           the D2H read of maxima / histograms / thresholds are inside the timed region.
   roofline : the dominant kernel of this repo (pq_hist2048_multi_f32, HBM-bound, 4 algorithmic
           bytes per element per launch), timed live with CUDA events on its launching stream.
-  cpu_baseline / --impl reference : the reference's CPU algorithm (the oracle port: torch CPU
-          forward + oracle/ statistics and KL, all host threads) on a bounded sample.
+  cpu_baseline / --impl reference : the UNMODIFIED reference (staged byte copy baseline/_ref, run by
+          baseline/ref_runner.py in its own process with DEVICE: cpu and WORKER_NUM = host cores) through its
+          own Quantity.activation_quantize on a bounded sample of the same workload ("kind": "reference");
+          falls back to the oracle port ("kind": "port") only if nothing is staged.
+Extra keys measured after the timed region (rank 0, N = 1): "c3_full" (the whole 8192-image job of BASELINE
+config 3, honest cache / re-forward split; every rank at any N), "recontest" (config 2), "reconmodel" (config 4)
+each with the reference's own modules timed eager on this same GPU, "c1" (config 1: this repo on the GPU next to
+the unmodified reference on the host cores, same 64 images).
 """
 import argparse
 import json
@@ -287,6 +293,13 @@ def ours(args):
     del host_batches
 
     fq_gbps, fq_ms = fakequant_bandwidth()
+    extras = {}
+    if not args.no_extras:
+        extras["c3_full"] = c3_full_job(net, workdir, rank, world)
+        torch.cuda.empty_cache()
+        if rank == 0 and world == 1:
+            extras.update(sim_extras(peak))
+            extras["c1"] = c1_extra()
     line = None
     if rank == 0:
         cpu = cpu_baseline(sample_images=args.cpu_sample) if world == 1 and not args.no_cpu_baseline else None
@@ -305,10 +318,178 @@ def ours(args):
                 "phases_s": {k: round(v, 4) for k, v in timings.items() if k.endswith("_s")}}
         if cpu:
             line["cpu_baseline"] = cpu
+        line.update(extras)
     if world > 1:
         torch.distributed.destroy_process_group()
     return line
 
+
+
+# ------------------------------------------------------------------------ extras (after the timed region)
+class CycledBatches:
+    """n_global batches of which this rank owns every world-th; the owned ones cycle through a small pool of
+    distinct pinned host batches (synthetic data: throughput does not depend on the pixel values)."""
+
+    def __init__(self, pool, n_global, rank, world):
+        self.pool, self.n, self.rank, self.world = pool, n_global, rank, world
+
+    def __iter__(self):
+        for i in range(self.n):
+            yield (self.pool[(i // self.world) % len(self.pool)], None) if i % self.world == self.rank else None
+
+
+def c3_full_job(net, workdir, rank, world, total_images=8192):
+    """BASELINE config 3 at its stated size: 8192 images = 128 micro-batches of 64 shared by the ranks, host batches,
+    through the public call.  At N = 1 the 550 GB of observed activations do not fit the HBM cache, so most of
+    pass 2 re-runs the forward; from N = 4 on everything is served from the cache."""
+    n_global = total_images // MICRO_BATCH
+    pool = [make_batch(50_000 + rank * 16 + i, pin=True) for i in range(min(16, n_global // world))]
+    secs, q = run_job(net, CycledBatches(pool, n_global, rank, world), n_global, workdir, rank, world)
+    t = q.timings
+    return {"images": total_images, "steps_per_rank": t["batches"], "seconds": round(secs, 3),
+            "images_per_s": round(total_images / secs, 1),
+            "pass2_from_hbm_cache": t["cached_batches"], "pass2_forward_reruns": t["batches"] - t["cached_batches"],
+            "cache_GB": round(t["cached_bytes"] / 1e9, 1),
+            "phases_s": {k: round(v, 3) for k, v in t.items() if k.endswith("_s")},
+            "inputs": "pinned host batches (H2D inside the timed region), %d distinct batches cycled" % len(pool)}
+
+
+def _sim_workdir(name, tag):
+    """Tables for the simulation extras: a short calibration of the same seeded model through this repo's tools."""
+    import tempfile
+    import ref_models
+    import tools
+    from common.quantity import merge_bn
+    workdir = tempfile.mkdtemp(prefix="pq_bench_%s_" % tag)
+    cfg, user = tool_configs(workdir, 2)
+    with torch.no_grad():
+        q = tools.Quantity(merge_bn(ref_models.build_model(name), "cpu"), config=cfg, user_config=user, verbose=False)
+        q.activation_quantize(ref_models.calib_batches(name, 2, 16))
+        q.weight_quantize()
+    return workdir, cfg
+
+
+def _rebuilt(name, mode, cfg):
+    import ref_models
+    import tools
+    with torch.no_grad():
+        r = tools.Reconstruction(ref_models.build_model(name), config=cfg)
+        r.merge_bn()
+        return getattr(r, mode)(r.get_quantity_information(), None).cuda().eval()
+
+
+def sim_extras(peak_hbm, iters=5):
+    """BASELINE configs 2 and 4 in the driver-run line: this repository's ReconTest / ReconModel forwards and, on
+    the same GPU in the same run, the reference's own modules run eager (baseline/ref_runner.py --device gpu)."""
+    import bench_sim
+    import ref_models
+    from common.quantity import enable_int8_pipeline
+    out = {}
+    # ---- config 2: ResNet-18 ReconTest, batch 256
+    B = 256
+    workdir, cfg = _sim_workdir("r18", "c2")
+    model = _rebuilt("r18", "ReconTest", cfg)
+    x = ref_models.eval_batch("r18", B).cuda()
+    ms, stats, launches, y = bench_sim.timed_forward(model, x, iters)
+    fq = stats.get("fakequant", {})
+    rec = {"workload": "ResNet-18 224x224 ReconTest (fake-quant) inference, batch %d" % B, "ms_per_forward": round(ms, 3),
+           "images_per_s": round(B / (ms * 1e-3), 1), "gpu_launches_per_forward": launches,
+           "fakequant_ms_per_forward": round(fq.get("ms_per_fwd", 0.0), 4)}
+    if fq.get("ms_per_fwd"):
+        rec["fakequant_GBps"] = round(fq["alg_bytes_per_fwd"] / (fq["ms_per_fwd"] * 1e-3) / 1e9, 1)
+        rec["fakequant_frac_of_hbm_peak"] = round(rec["fakequant_GBps"] / peak_hbm, 4)
+    if reference_staged():
+        res, arrays = run_reference("r18", "c2", "--device", "gpu", "--tables-from", workdir, "--recon", "ReconTest",
+                                    "--eval", B, "--time-forward", iters)
+        rec["reference_eager_ms"] = round(statistics.median(res["ReconTest/forward_ms"]), 3)
+        rec["reference_build_s"] = round(res["seconds_build_ReconTest"], 1)
+        rec["logits_equal_reference"] = bool(np.array_equal(np.load(arrays)["ReconTest/y"], y.cpu().numpy()))
+    out["recontest"] = rec
+    del model, x, y
+    torch.cuda.empty_cache()
+    # ---- config 4: ResNet-50 ReconModel, batch 512
+    B = 512
+    workdir, cfg = _sim_workdir("r50", "c4")
+    model = _rebuilt("r50", "ReconModel", cfg)
+    x = ref_models.eval_batch("r50", B).cuda()
+    ms32, stats32, launches32, y32 = bench_sim.timed_forward(model, x, iters)
+    enable_int8_pipeline(model, True)
+    ms8, stats8, launches8, y8 = bench_sim.timed_forward(model, x, iters)
+    gms, glaunches, gy = bench_sim.timed_graph(model, x, iters)
+    peak8 = bench_sim.int8_peak_tops()
+    rec = {"workload": "ResNet-50 224x224 ReconModel (integer simulation) inference, batch %d" % B,
+           "fp32_boundary_ms_per_forward": round(ms32, 3), "int8_pipeline_ms_per_forward": round(ms8, 3),
+           "int8_pipeline_graph_ms_per_forward": round(gms, 3), "images_per_s": round(B / (gms * 1e-3), 1),
+           "gpu_launches_per_forward": launches8, "int8_peak_TOPS_measured": round(peak8, 1),
+           "pipeline_equals_fp32_boundary": bool(torch.equal(y8, y32) and torch.equal(gy, y32)), "kernels": {}}
+    ops = ms_conv = 0.0
+    for kname, st in stats8.items():
+        k = {"launches": st["launches_per_fwd"], "ms": round(st["ms_per_fwd"], 4)}
+        if kname in ("conv_s8", "gemm_s8", "conv_add_s8"):
+            ops += st["alg_bytes_per_fwd"]
+            ms_conv += st["ms_per_fwd"]
+            k["TOPS"] = round(st["alg_bytes_per_fwd"] / (st["ms_per_fwd"] * 1e-3) / 1e12, 1)
+        elif st["ms_per_fwd"] > 0:
+            k["GBps"] = round(st["alg_bytes_per_fwd"] / (st["ms_per_fwd"] * 1e-3) / 1e9, 1)
+            k["frac_of_hbm_peak"] = round(k["GBps"] / peak_hbm, 4)
+        rec["kernels"][kname] = k
+    if ms_conv > 0:
+        rec["conv_ms_per_forward"] = round(ms_conv, 3)
+        rec["conv_TOPS"] = round(ops / (ms_conv * 1e-3) / 1e12, 1)
+        rec["frac_of_int8_peak"] = round(rec["conv_TOPS"] / peak8, 4)
+    if reference_staged():
+        res, arrays = run_reference("r50", "c4", "--device", "gpu", "--tables-from", workdir, "--recon",
+                                    "ReconModel,ReconModel:nocudnn", "--eval", B, "--time-forward", iters)
+        rec["reference_eager_ms"] = round(statistics.median(res["ReconModel/forward_ms"]), 3)
+        ref_y = np.load(arrays)
+        # the exact arm (cuDNN's fp32 Winograd is not exact on integers, see tests/test_gpu_vs_reference.py)
+        rec["logits_equal_reference_exact_conv"] = bool(np.array_equal(ref_y["ReconModel:nocudnn/y"], y32.cpu().numpy()))
+        rec["logits_equal_reference_cudnn"] = bool(np.array_equal(ref_y["ReconModel/y"], y32.cpu().numpy()))
+    out["reconmodel"] = rec
+    del model, x
+    torch.cuda.empty_cache()
+    return out
+
+
+def c1_extra():
+    """BASELINE config 1 (ResNet-18, 64 images as 8 batches of 8): this repository on the GPU next to the UNMODIFIED
+    reference on the host cores, both running the whole job (calibration + weight quantisation + rewrite)."""
+    import tempfile
+    import ref_models
+    import tools
+    from common.quantity import merge_bn
+    workdir = tempfile.mkdtemp(prefix="pq_bench_c1_")
+    cfg, user = tool_configs(workdir, 8)
+    batches = ref_models.calib_batches("r18", 8, 8)
+    with torch.no_grad():
+        net = merge_bn(ref_models.build_model("r18"), "cpu")
+        for _ in range(2):                                  # second run: warm allocator / kernels
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            q = tools.Quantity(net, config=cfg, user_config=user, verbose=False)
+            q.activation_quantize(batches)
+            torch.cuda.synchronize()
+            t_act = time.perf_counter() - t0
+            q.weight_quantize()
+            t_all = time.perf_counter() - t0
+    rec = {"workload": "ResNet-18 224x224 calibration, 64 images (8 batches of 8), feat.table + weight.table + JSON",
+           "ours_activation_quantize_s": round(t_act, 3), "ours_whole_job_s": round(t_all, 3),
+           "ours_images_per_s": round(64 / t_act, 1)}
+    if reference_staged():
+        res, _ = run_reference("r18", "c1", "--device", "cpu", "--calib", "8x8")
+        ours_feat = open(cfg["OUTPUT"]["FEAT_BIT_TABLE"]).read()
+        ours_weight = open(cfg["OUTPUT"]["WEIGHT_BIT_TABLE"]).read()
+        ref_feat = res["after_weight_quantize"]["feat.table"]
+        rec.update({
+            "reference_cpu_activation_quantize_s": round(res["seconds_activation_quantize"], 1),
+            "reference_cpu_weight_quantize_s": round(res["seconds_weight_quantize"], 1),
+            "reference_cpu_images_per_s": round(64 / res["seconds_activation_quantize"], 2),
+            "reference_cores": res["worker_num"], "host_cores": os.cpu_count(),
+            "weight_table_identical": ours_weight == res["after_second_rewrite"]["weight.table"],
+            # cuDNN forward here, MKLDNN forward there: byte-identity of feat.table is asserted GPU-vs-GPU in the tests
+            "feat_table_lines_differing_vs_cpu_forward": sum(a != b for a, b in zip(ours_feat.split("\n"),
+                                                                                      ref_feat.split("\n")))})
+    return rec
 
 # ------------------------------------------------------------------- CPU baseline / reference arm
 def cpu_calibration_sample(n_images, batch, threads):
@@ -359,21 +540,69 @@ def cpu_calibration_sample(n_images, batch, threads):
     return secs, len(batches) * batch
 
 
-def cpu_baseline(sample_images=16):
-    threads = os.cpu_count() or 1
-    secs, n = cpu_calibration_sample(sample_images, min(8, sample_images), threads)
-    return {"value": round(n / secs, 3), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d images (2 batches of 8) through torch-CPU fp32 forward x2 + oracle max-abs/hist "
-                      "+ oracle KL search of 71 tensors; the reference itself is pure Python and is slower "
-                      "(C1 golden run: 1.6 images/s on 8 cores)" % n}
+RUNNER = os.path.join(REPO, "baseline", "ref_runner.py")
+
+
+def reference_staged():
+    return os.path.isdir(os.path.join(REPO, "baseline", "_ref", "quantity", "common", "quantity"))
+
+
+def run_reference(model, out_tag, *flags, timeout=1500):
+    """baseline/ref_runner.py (the unmodified reference) in its own process; returns (result.json, arrays path)."""
+    import tempfile
+    out = tempfile.mkdtemp(prefix="pq_ref_%s_" % out_tag)
+    cmd = [sys.executable, RUNNER, "--model", model, "--out", out] + [str(f) for f in flags]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError("reference runner failed: " + p.stdout[-1500:])
+    with open(os.path.join(out, "result.json")) as f:
+        return json.load(f), os.path.join(out, "arrays.npz")
+
+
+def reference_calibration(n_batches, batch, warmup=0):
+    """The reference's own two-pass calibration job (Quantity.activation_quantize, pytorch_quantizer.py:345-489:
+    fp32 CPU forward x2, numpy max-abs, the per-element Python histogram loop in a process pool, the pure-Python
+    KL search of all 71 tensors) on n_batches x batch synthetic images of the bench workload."""
+    res, _ = run_reference("r50", "calib", "--device", "cpu", "--calib", "%dx%d" % (n_batches, batch),
+                           "--calib-only-activations", "--warmup-batches", warmup)
+    return res["seconds_activation_quantize"], n_batches * batch, res["worker_num"]
+
+
+def cpu_baseline(sample_images=8):
+    if not reference_staged():
+        threads = os.cpu_count() or 1
+        secs, n = cpu_calibration_sample(16, 8, threads)
+        return {"value": round(n / secs, 3), "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "%d images through torch-CPU fp32 forward x2 + oracle max-abs/hist + oracle KL search "
+                          "(baseline/_ref not staged)" % n}
+    secs, n, workers = reference_calibration(max(1, sample_images // 2), 2)
+    return {"value": round(n / secs, 3), "unit": UNIT, "cores": workers, "kind": "reference",
+            "sample": "the unmodified reference (baseline/_ref, DEVICE: cpu, WORKER_NUM %d of %d host cores): one whole "
+                      "Quantity.activation_quantize job on %d images (%d batches of 2) of the same ResNet-50 workload, "
+                      "%.1f s" % (workers, os.cpu_count() or 1, n, n // 2, secs)}
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return None
-    threads = os.cpu_count() or 1
     K, W = args.steps, max(args.warmup, 1)
+    if reference_staged():
+        per_step = 2                                   # bounded sample: a step is one batch of 2 images
+        secs, n, workers = reference_calibration(K, per_step, warmup=W)
+        value = round(n / secs, 3)
+        return {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": W,
+            "ms_per_step": round(secs * 1e3 / K, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_images_per_step": per_step,
+                       "job": "one whole activation_quantize job of %d batches (both passes + KL search of 71 tensors)" % K},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference",
+                             "sample": "unmodified reference (baseline/_ref), DEVICE: cpu, WORKER_NUM %d: %d steps of %d "
+                                       "images, %d warm-up forwards" % (workers, K, per_step, W)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    threads = os.cpu_count() or 1
     per_step = 8                                       # bounded sample: 8 images per step
     for _ in range(min(W, 1)):
         cpu_calibration_sample(per_step, per_step, threads)
@@ -398,8 +627,9 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=16)
+    ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip c3_full / recontest / reconmodel / c1")
     args = ap.parse_args()
     # the drop-in classes print progress like the reference does; keep stdout to the ONE JSON line
     real_stdout = sys.stdout

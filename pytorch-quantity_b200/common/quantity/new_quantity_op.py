@@ -32,6 +32,23 @@ from . import _native
 QUANTIZE_BIT = 8                     # new_quantity_op.py:8
 WRITE_DIAGNOSTICS = False
 
+# Debug switch for the reference's own exactness limit.  The reference runs the integer convolution as an fp32
+# nn.Conv2d on integer-valued tensors (new_quantity_op.py:124-126), which equals int8 x int8 -> int32 only while
+# every partial sum stays below 2^24 (and only if the library's convolution is exact: cuDNN's fp32 Winograd is
+# not, see tests/test_gpu_vs_reference.py).  The kernels here accumulate in int32 and are always exact, so beyond
+# that limit they would legitimately DIFFER from the reference.  With CHECK_ACC_RANGE on, NewConv2d / NewLinear
+# re-evaluate their accumulator exactly (float64, slow) on every forward, keep ``max_abs_acc`` on the module and
+# warn when it reaches 2^24, so that such a mismatch is explained rather than mysterious.
+CHECK_ACC_RANGE = False
+FP32_EXACT_LIMIT = 1 << 24
+
+
+def accumulator_report(model):
+    """name -> max |accumulator| seen by every NewConv2d / NewLinear of ``model`` (after forwards run with
+    CHECK_ACC_RANGE on); names whose value reached 2^24 are where the reference's fp32 arithmetic stops being
+    integer arithmetic."""
+    return {name: m.max_abs_acc for name, m in model.named_modules() if getattr(m, "max_abs_acc", None) is not None}
+
 
 def _range(bits):
     assert bits == 8 or bits == 16, "Not support bit width."
@@ -108,6 +125,27 @@ def _pad32(c):
 
 
 class _IntSimBase(nn.Module):
+    max_abs_acc = None
+
+    def _check_acc(self, input, layer):
+        """Debug path (CHECK_ACC_RANGE): exact float64 re-evaluation of this layer's accumulator."""
+        import warnings
+        import torch.nn.functional as F
+        x = input.dequantize() if hasattr(input, "dequantize") else input
+        with torch.no_grad():
+            q = torch.clamp(torch.round(x.float() * 2.0 ** self.input_bit), -128.0, 127.0).double()
+            w = layer.weight.detach().double()                     # integer-valued after quantity()
+            if isinstance(layer, nn.Conv2d):
+                acc = F.conv2d(q, w, None, layer.stride, layer.padding, layer.dilation, layer.groups)
+            else:
+                acc = F.linear(q, w)
+            m = float(acc.abs().max()) if acc.numel() else 0.0
+        self.max_abs_acc = max(self.max_abs_acc or 0.0, m)
+        if m >= FP32_EXACT_LIMIT:
+            warnings.warn("%s: |accumulator| reaches %.4g >= 2^24: the reference's fp32 convolution is no longer "
+                          "exact integer arithmetic here, so its output may differ from this (exact int32) result"
+                          % (type(self).__name__, m))
+
     def _read_info(self, quantize_infor):
         self.weight_bit = quantize_infor["weight_bit"]
         self.bias_bit = quantize_infor["bias_bit"]
@@ -183,6 +221,8 @@ class NewConv2d(_IntSimBase):
         self.register_buffer("_w_krsc", w_krsc.contiguous())
 
     def forward(self, input):
+        if CHECK_ACC_RANGE:
+            self._check_acc(input, self.Conv)
         if getattr(self, "int8_pipeline", False):
             from .int8_pipeline import conv_forward
             return conv_forward(self, input)
@@ -238,6 +278,8 @@ class NewLinear(_IntSimBase):
         self.register_buffer("_w_nk", w.contiguous())
 
     def forward(self, input):
+        if CHECK_ACC_RANGE:
+            self._check_acc(input, self.Linear)
         x2 = input.reshape(-1, input.shape[-1])
         # Quan: a [B][K] matrix is NCHW with H = W = 1, so the same kernel quantises and pads it
         q = _native.quantize_nchw_to_nhwc_s8(x2.view(x2.shape[0], x2.shape[1], 1, 1), self.input_bit,

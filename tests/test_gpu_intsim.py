@@ -212,3 +212,32 @@ def test_folded_bias_epilogue_equals_classic(oracle, M, N, K, rs, relu):
     f32a, _ = _native.gemm_s8(ta, tw, tb, rs, 3, want_f32=True, want_s8=False)
     f32b, _ = _native.gemm_s8(ta, tw, folded_bias, rs, 3, want_f32=True, want_s8=False)
     assert torch.equal(f32a, f32b)
+
+
+def test_accumulator_range_debug_check():
+    """CHECK_ACC_RANGE (debug): the reference's fp32 convolution is integer arithmetic only below 2^24
+    (SURVEY a13); the check records max |acc| per layer and warns where a legitimate divergence can start."""
+    import warnings
+    import common.quantity as cq
+    from common.quantity import new_quantity_op as nq
+    info = {"weight_bit": 7, "input_bit": 7, "output_bit": 0, "bias_bit": 0}
+    conv = nn.Conv2d(512, 16, 3, padding=1, bias=False)
+    with torch.no_grad():
+        conv.weight.fill_(1.0)                                     # quantises to +127 everywhere
+        m = cq.NewConv2d(conv.cuda(), dict(info))
+        x = torch.ones(1, 512, 8, 8, device="cuda")                # quantises to +127 everywhere
+        small = cq.NewConv2d(nn.Conv2d(16, 16, 1).cuda(), {"weight_bit": 5, "input_bit": 3, "output_bit": 3, "bias_bit": 3})
+        nq.CHECK_ACC_RANGE = True
+        try:
+            with warnings.catch_warnings(record=True) as w:
+                warnings.simplefilter("always")
+                y = m(x)
+                small(torch.randn(2, 16, 4, 4, device="cuda"))
+        finally:
+            nq.CHECK_ACC_RANGE = False
+    assert m.max_abs_acc == 127.0 * 127.0 * 512 * 9 and m.max_abs_acc >= nq.FP32_EXACT_LIMIT     # 74 317 824
+    assert any("2^24" in str(v.message) for v in w)
+    assert 0 < small.max_abs_acc < nq.FP32_EXACT_LIMIT
+    assert float(y.max()) == 127.0                                 # the int32 path itself stays exact and saturates
+    model = nn.Sequential(m, small)
+    assert set(nq.accumulator_report(model)) == {"0", "1"}
