@@ -75,6 +75,9 @@ def main():
     ap.add_argument("--dump-layers", action="store_true")
     ap.add_argument("--time-forward", type=int, default=0, help="time this many forwards of each rebuilt model")
     ap.add_argument("--workers", type=int, default=0)
+    ap.add_argument("--exact-batch", type=int, default=0,
+                    help="':nocudnn' variants forward only the first N images of the evaluation batch (ATen's GEMM "
+                         "convolution loops over the samples and is slow at batch 512)")
     ap.add_argument("--self-check", action="store_true",
                     help="per NewConv2d / NewLinear: compare the reference's own fp32 accumulator with an exact float64 "
                          "evaluation of the same integer operands (is the library's fp32 conv exact on this device?)")
@@ -253,8 +256,12 @@ def main():
                     if type(mod).__name__ in LAYER_TYPES:
                         hooks.append(mod.register_forward_hook(keep(lname)))
                 import contextlib
-                lib = torch.backends.cudnn.flags(enabled=False) if no_cudnn else contextlib.nullcontext()
-                with lib:
+
+                def lib():
+                    return torch.backends.cudnn.flags(enabled=False) if no_cudnn else contextlib.nullcontext()
+                if variant == "nocudnn" and args.exact_batch:
+                    x = x[:args.exact_batch]
+                with lib():
                     y = model(x.clone())
                 for h in hooks:
                     h.remove()
@@ -262,14 +269,14 @@ def main():
                     result[spec + "/self_check"] = self_check
                 arrays[spec + "/y"] = y.cpu().numpy()
                 result[spec + "/layer_md5"] = layer_md5
-                if args.time_forward:
+                if args.time_forward and variant != "nocudnn":      # the stock (cuDNN) path is what gets timed
                     times = []
                     for it in range(args.time_forward + 2):
                         if gpu:
                             torch.cuda.synchronize()
                             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                             s.record()
-                            with lib:
+                            with lib():
                                 model(x)
                             e.record()
                             torch.cuda.synchronize()

@@ -40,7 +40,8 @@ typedef void *pq_stream_t; /* cudaStream_t */
 #define PQ_EALIGN (-3)       /* pointer not aligned as documented */
 #define PQ_ETOOMANY (-4)     /* more segments than PQ_MAX_SEGMENTS in one call */
 
-#define PQ_HIST_BINS 2048   /* tools/configs.yml:23 INTERVAL_NUM */
+#define PQ_HIST_BINS 2048   /* tools/configs.yml:23 INTERVAL_NUM (the default; the fast histogram kernel) */
+#define PQ_HIST_BINS_MAX 8192 /* largest INTERVAL_NUM the generic entry points accept */
 #define PQ_KL_TARGET_BIN 128 /* common/quantity/quantizer.py:98 target_bin */
 #define PQ_KL_CANDIDATES (PQ_HIST_BINS - PQ_KL_TARGET_BIN)
 #define PQ_MAX_SEGMENTS 256 /* tensors per multi-tensor launch */
@@ -85,6 +86,19 @@ int pq_hist2048_multi_f32(const float *const *xs_host, const uint64_t *ns_host,
 size_t pq_kl_workspace_doubles(void);
 int pq_kl_search_f64(const double *counts, int k, double *workspace, double *kl,
                      int *threshold, pq_stream_t stream);
+
+/* ---- a3 / a5 / a6 for any INTERVAL_NUM (tools/configs.yml:23; DistributionCollector(interval_num=...),
+ * common/quantity/distribution_collector.py:9-22, and `length = distribution.size` in
+ * common/quantity/quantizer.py:98-103).  nbins == 2048 forwards to the specialised entry points above.
+ * pq_hist_multi_f32: hist is int64 [k][nbins], 1 <= nbins <= PQ_HIST_BINS_MAX (else PQ_EUNSUPPORTED).
+ * pq_kl_search_n_f64: counts fp64 [k][nbins], kl (optional) fp64 [k][nbins - 128], 128 < nbins <=
+ * PQ_HIST_BINS_MAX (nbins <= 128: PQ_EINVAL -- the reference's candidate loop would be empty), default
+ * threshold nbins - 1; workspace fp64 [k][pq_kl_workspace_doubles_n(nbins)]. */
+int pq_hist_multi_f32(const float *const *xs_host, const uint64_t *ns_host, const float *intervals_host,
+                      int k, int nbins, long long *hist, pq_stream_t stream);
+size_t pq_kl_workspace_doubles_n(int nbins);
+int pq_kl_search_n_f64(const double *counts, int k, int nbins, double *workspace, double *kl,
+                       int *threshold, pq_stream_t stream);
 
 /* ---- a10 / a12: QuanDequan.forward (new_quantity_op.py:246-257) and Quantity.forward (:48-58)
  * y = clamp(rint_half_even(x * 2^bit), lo, hi) [/ 2^bit when dequant != 0].  y must not alias x
@@ -177,6 +191,16 @@ int pq_gemm_s8_ex(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M
 int pq_conv2d_s8_ex(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
                     const pq_conv_desc *desc_host, int flags, float *out_f32_nchw, int8_t *out_s8_nhwc,
                     pq_stream_t stream);
+
+/* Dilated convolution (nn.Conv2d(dilation=...) wrapped by NewConv2d, new_quantity_op.py:104-133; the reference's
+ * weight path zero-stuffs such kernels for its target hardware, tools/pytorch_quantizer.py:626-629,679-693).
+ * Same contract as pq_conv2d_s8_ex with filter tap (r, s) reading input pixel
+ * (p*stride_h - pad_h + r*dil_h, q*stride_w - pad_w + s*dil_w); desc->P / Q must be the dilated output size
+ * (H + 2*pad_h - ((R-1)*dil_h + 1)) / stride_h + 1.  The taps are im2col-TMA offsets, so no multiply is wasted
+ * on stuffed zeros.  A 1x1 filter ignores the dilation. */
+int pq_conv2d_s8_dil(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
+                     const pq_conv_desc *desc_host, int dil_h, int dil_w, int flags, float *out_f32_nchw,
+                     int8_t *out_s8_nhwc, pq_stream_t stream);
 
 int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const int32_t *bias_q,
                         const pq_conv_desc *desc_host, int Hp, int Wp, int flags, float *out_f32_nchw,

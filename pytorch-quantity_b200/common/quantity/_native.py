@@ -15,6 +15,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__fi
 LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libpq_sm100.so")
 
 HIST_BINS = 2048
+HIST_BINS_MAX = 8192
 KL_TARGET_BIN = 128
 KL_CANDIDATES = HIST_BINS - KL_TARGET_BIN
 MAX_SEGMENTS = 256
@@ -29,6 +30,9 @@ SYMBOLS = {
     "pq_hist2048_multi_f32": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "pq_kl_workspace_doubles": (_sz, []),
     "pq_kl_search_f64": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "pq_hist_multi_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "pq_kl_workspace_doubles_n": (_sz, [_i]),
+    "pq_kl_search_n_f64": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "pq_fakequant_f32": (_i, [_vp, _vp, _sz, _i, _f, _f, _i, _vp]),
     "pq_add_clamp_f32": (_i, [_vp, _vp, _vp, _sz, _f, _f, _vp]),
     "pq_rshift_f32": (_i, [_vp, _vp, _sz, _i, _f, _f, _vp]),
@@ -41,6 +45,7 @@ SYMBOLS = {
     "pq_conv2d_s8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pq_gemm_s8_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pq_conv2d_s8_ex": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "pq_conv2d_s8_dil": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pq_gemm_s8_add": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pq_conv2d_s8_add": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "pq_relu_s8": (_i, [_vp, _vp, _sz, _vp]),
@@ -194,31 +199,38 @@ def absmax_per_channel(x, max_bits, channel_dim=1):
 
 
 def hist_multi(tensors, intervals, hist):
-    """hist (int64 CUDA [k][2048]) += 2048-bin |x| histograms with per-tensor fp32 bin width."""
+    """hist (int64 CUDA [k][nbins]) += nbins-bin |x| histograms with per-tensor fp32 bin width
+    (nbins = hist.shape[1]: 2048 takes the specialised kernel, anything else up to 8192 the generic one)."""
+    nbins = int(hist.shape[1])
     for lo in range(0, len(tensors), MAX_SEGMENTS):
         part = tensors[lo:lo + MAX_SEGMENTS]
         ptrs, ns = _seg_arrays(part)
         iv = (ctypes.c_float * len(part))(*[float(v) for v in intervals[lo:lo + len(part)]])
         out = hist[lo:lo + len(part)]
         with _Timed("hist", 1, 4 * sum(t.numel() for t in part), hist.device):
-            check(lib().pq_hist2048_multi_f32(ptrs, ns, iv, len(part), out.data_ptr(), _stream(hist)),
-                  "pq_hist2048_multi_f32")
+            if nbins == HIST_BINS:
+                check(lib().pq_hist2048_multi_f32(ptrs, ns, iv, len(part), out.data_ptr(), _stream(hist)),
+                      "pq_hist2048_multi_f32")
+            else:
+                check(lib().pq_hist_multi_f32(ptrs, ns, iv, len(part), nbins, out.data_ptr(), _stream(hist)),
+                      "pq_hist_multi_f32 (INTERVAL_NUM=%d)" % nbins)
 
 
 def kl_search(counts_f64, want_curves=False):
-    """counts_f64: CUDA fp64 [k][2048].  Returns (threshold int32 [k], kl fp64 [k][1920] or None)."""
+    """counts_f64: CUDA fp64 [k][nbins].  Returns (threshold int32 [k], kl fp64 [k][nbins - 128] or None)."""
     require_cuda(counts_f64, "kl_search")
-    assert counts_f64.dtype == torch.float64 and counts_f64.dim() == 2 and counts_f64.shape[1] == HIST_BINS
+    assert counts_f64.dtype == torch.float64 and counts_f64.dim() == 2
+    nbins = int(counts_f64.shape[1])
     counts_f64 = counts_f64.contiguous()
     k = counts_f64.shape[0]
     dev = counts_f64.device
-    ws = torch.empty(k * lib().pq_kl_workspace_doubles(), dtype=torch.float64, device=dev)
+    ws = torch.empty(k * lib().pq_kl_workspace_doubles_n(nbins), dtype=torch.float64, device=dev)
     thr = torch.empty(k, dtype=torch.int32, device=dev)
-    kl = torch.empty((k, KL_CANDIDATES), dtype=torch.float64, device=dev) if want_curves else None
+    kl = torch.empty((k, max(nbins - KL_TARGET_BIN, 0)), dtype=torch.float64, device=dev) if want_curves else None
     with _Timed("kl", 3, 8 * counts_f64.numel(), dev):
-        check(lib().pq_kl_search_f64(counts_f64.data_ptr(), k, ws.data_ptr(),
-                                     kl.data_ptr() if want_curves else None, thr.data_ptr(),
-                                     _stream(counts_f64)), "pq_kl_search_f64")
+        check(lib().pq_kl_search_n_f64(counts_f64.data_ptr(), k, nbins, ws.data_ptr(),
+                                       kl.data_ptr() if want_curves else None, thr.data_ptr(),
+                                       _stream(counts_f64)), "pq_kl_search_n_f64 (INTERVAL_NUM=%d)" % nbins)
     return thr, kl
 
 
@@ -364,20 +376,28 @@ def gemm_s8(a, w, bias_q, rs, ob, hw=1, want_f32=True, want_s8=False, k_real=Non
 
 
 def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, want_s8=False, c_real=None,
-              relu=False):
+              relu=False, dilation=(1, 1)):
     require_cuda(x_nhwc, "conv2d_s8")
     N, H, W, C = x_nhwc.shape
     K, R, S, C2 = w_krsc.shape
     assert C == C2
-    P = (H + 2 * padding[0] - R) // stride[0] + 1
-    Q = (W + 2 * padding[1] - S) // stride[1] + 1
+    dh, dw = (int(dilation[0]), int(dilation[1])) if (R, S) != (1, 1) else (1, 1)
+    P = (H + 2 * padding[0] - ((R - 1) * dh + 1)) // stride[0] + 1
+    Q = (W + 2 * padding[1] - ((S - 1) * dw + 1)) // stride[1] + 1
     d = ConvDesc(N, H, W, C, K, R, S, stride[0], stride[1], padding[0], padding[1], P, Q, int(rs), int(ob))
     out_f32 = torch.empty((N, K, P, Q), dtype=torch.float32, device=x_nhwc.device) if want_f32 else None
     out_s8 = torch.empty((N, P, Q, K), dtype=torch.int8, device=x_nhwc.device) if want_s8 else None
     with _Timed("conv_s8", 1, 2 * N * P * Q * K * R * S * (c_real or C), x_nhwc.device):   # int8 ops
-        check(lib().pq_conv2d_s8_ex(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
-                                    _bias_flags(bias_q, K, relu), out_f32.data_ptr() if want_f32 else None,
-                                    out_s8.data_ptr() if want_s8 else None, _stream(x_nhwc)), "pq_conv2d_s8")
+        if (dh, dw) == (1, 1):
+            check(lib().pq_conv2d_s8_ex(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
+                                        _bias_flags(bias_q, K, relu), out_f32.data_ptr() if want_f32 else None,
+                                        out_s8.data_ptr() if want_s8 else None, _stream(x_nhwc)), "pq_conv2d_s8")
+        else:
+            check(lib().pq_conv2d_s8_dil(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
+                                         dh, dw, _bias_flags(bias_q, K, relu),
+                                         out_f32.data_ptr() if want_f32 else None,
+                                         out_s8.data_ptr() if want_s8 else None, _stream(x_nhwc)),
+                  "pq_conv2d_s8_dil (dilation %dx%d)" % (dh, dw))
     return out_f32, out_s8
 
 

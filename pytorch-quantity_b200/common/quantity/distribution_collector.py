@@ -25,9 +25,12 @@ class DistributionCollector:
 
     def __init__(self, tensor_list, interval_num=2048, statistic=1, worker_num=1, debug=False,
                  device=None):
-        if interval_num != _native.HIST_BINS:
-            raise ValueError("the sm_100a histogram kernel is built for INTERVAL_NUM=2048, got %r"
-                             % (interval_num,))
+        # INTERVAL_NUM is a configuration value in the reference (tools/configs.yml:23); 2048 runs the specialised
+        # histogram kernel, any other count up to 8192 the generic one
+        if int(interval_num) != interval_num or not (1 <= interval_num <= _native.HIST_BINS_MAX):
+            raise ValueError("INTERVAL_NUM must be an integer in [1, %d] (PQ_EUNSUPPORTED beyond: shared-memory "
+                             "histogram), got %r" % (_native.HIST_BINS_MAX, interval_num))
+        interval_num = int(interval_num)
         self._tensor_list = tensor_list
         self._interval_num = interval_num
         self._statistic = statistic

@@ -77,7 +77,7 @@ class _LazyAdd:
     def _fusable(t):
         lc = t._lazy_conv
         return FUSE_ADD_INTO_CONV and lc is not None and lc.q is not None and not lc.out and not t.relu_pending \
-            and lc.mod.Conv.out_channels % 16 == 0
+            and lc.mod.Conv.out_channels % 16 == 0 and getattr(lc.mod, "_dilation", (1, 1)) == (1, 1)
 
     def get(self, relu, kind):
         """kind: "s16" (exact sum) or "q8" (Quantity(q_bit) of it).  Returns the dict of payloads held."""
@@ -354,12 +354,13 @@ def conv_forward(mod, x):
         q = _native.quantize_nchw_to_nhwc_s8(x, mod.input_bit, mod._c_pad)
     N, H, W, _ = q.shape
     (R, S), (sh, sw), (ph, pw) = conv.kernel_size, conv.stride, conv.padding
-    P, Q = (H + 2 * ph - R) // sh + 1, (W + 2 * pw - S) // sw + 1
+    dh, dw = getattr(mod, "_dilation", (1, 1))
+    P, Q = (H + 2 * ph - ((R - 1) * dh + 1)) // sh + 1, (W + 2 * pw - ((S - 1) * dw + 1)) // sw + 1
 
     def run_conv(relu, q=q):
         return _native.conv2d_s8(q, mod._w_krsc, mod._bias_i32, conv.stride, conv.padding, mod.rs_bit,
                                  mod.output_bit, want_f32=False, want_s8=True, c_real=conv.in_channels,
-                                 relu=relu)[1]
+                                 relu=relu, dilation=getattr(mod, "_dilation", (1, 1)))[1]
     # deferred: the ReLU that may follow is fused on demand, and a NewAdd consumer can absorb the whole convolution
     return QTensor((N, conv.out_channels, P, Q), q.device, q8_bit=mod.output_bit,
                    lazy_conv=_LazyConv(mod, run_conv, q))

@@ -194,16 +194,26 @@ class NewConv2d(_IntSimBase):
 
     def quantity(self):
         conv = self.Conv
-        if conv.groups != 1 or conv.dilation not in ((1, 1), 1) or conv.padding_mode != "zeros":
-            raise NotImplementedError("NewConv2d: groups=1, dilation=1, zero padding only")
+        if conv.padding_mode != "zeros" or isinstance(conv.padding, str):
+            raise NotImplementedError(
+                "NewConv2d(%r): padding_mode=%r / padding=%r is not supported by the sm_100a convolution kernels "
+                "(PQ_EUNSUPPORTED: zero padding given as integers only; there is no CPU fallback)"
+                % (conv, conv.padding_mode, conv.padding))
         wq = self._quantize_params(conv, conv.out_channels)
         K, C, R, S = wq.shape
+        self._dilation = tuple(int(d) for d in conv.dilation) if (R, S) != (1, 1) else (1, 1)
+        dilated = self._dilation != (1, 1)
+        self._group_convs = None
+        if conv.groups != 1:
+            self._build_groups(conv, wq)
+            return
         # im2col TMA fetches channel blocks of 32 / 64 / 128 bytes; a 1x1 stride-1 conv is a plain GEMM
         plain = (R, S) == (1, 1) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (0, 0)
         # very few input channels (the ResNet stem): instead of padding C to 32, either the windowed
         # small-channel kernel (8-byte pixels, one TMA per filter row) or explicit im2col + GEMM
-        self._smallc = (not plain) and C <= 8 and S <= 8 and conv.stride[1] % 2 == 0
-        self._explicit_im2col = (not plain) and C <= 8 and not self._smallc
+        # (a dilated filter always takes the im2col-TMA kernel: its taps are TMA offsets)
+        self._smallc = (not plain) and not dilated and C <= 8 and S <= 8 and conv.stride[1] % 2 == 0
+        self._explicit_im2col = (not plain) and not dilated and C <= 8 and not self._smallc
         if self._smallc:
             w = torch.zeros((K, R, 8, 8), dtype=torch.int8, device=wq.device)       # [K][R][tap slot][channel slot]
             w[:, :, :S, :C] = wq.permute(0, 2, 3, 1).to(torch.int8)
@@ -220,9 +230,35 @@ class NewConv2d(_IntSimBase):
         w_krsc[..., :C] = wq.permute(0, 2, 3, 1).to(torch.int8)
         self.register_buffer("_w_krsc", w_krsc.contiguous())
 
+    def _build_groups(self, conv, wq):
+        """groups > 1 (the reference wraps any nn.Conv2d, new_quantity_op.py:104-133): one integer convolution per
+        group over its channel slice, built from the already quantised parameters, results concatenated along the
+        channel axis -- exactly the definition of a grouped convolution, every group on the tensor-core kernels."""
+        G = conv.groups
+        Kg, Cg = conv.out_channels // G, conv.in_channels // G
+        subs = []
+        for g in range(G):
+            sub = nn.Conv2d(Cg, Kg, conv.kernel_size, conv.stride, conv.padding, conv.dilation, 1, True).to(wq.device)
+            with torch.no_grad():
+                # integer-valued parameters scaled back by exact powers of two: re-quantising them is the identity
+                sub.weight.copy_(wq[g * Kg:(g + 1) * Kg] * 2.0 ** -self.weight_bit)
+                sub.bias.copy_(self.quantized_bias[g * Kg:(g + 1) * Kg] * 2.0 ** -self.bias_bit)
+            subs.append(NewConv2d(sub, {"weight_bit": self.weight_bit, "bias_bit": self.bias_bit,
+                                        "input_bit": self.input_bit, "output_bit": self.output_bit}))
+        self._group_convs = nn.ModuleList(subs)
+        self._smallc = self._explicit_im2col = False
+
+    def _grouped_forward(self, input):
+        x = input.dequantize() if hasattr(input, "dequantize") else input
+        Cg = self.Conv.in_channels // self.Conv.groups
+        outs = [sub(x[:, g * Cg:(g + 1) * Cg].contiguous()) for g, sub in enumerate(self._group_convs)]
+        return torch.cat(outs, 1)
+
     def forward(self, input):
         if CHECK_ACC_RANGE:
             self._check_acc(input, self.Conv)
+        if getattr(self, "_group_convs", None) is not None:
+            return self._grouped_forward(input)
         if getattr(self, "int8_pipeline", False):
             from .int8_pipeline import conv_forward
             return conv_forward(self, input)
@@ -238,8 +274,8 @@ class NewConv2d(_IntSimBase):
             return out.view(N, conv.out_channels, P, Q)
         q = _native.quantize_nchw_to_nhwc_s8(input, self.input_bit, self._c_pad)        # Quan
         out, _ = _native.conv2d_s8(q, self._w_krsc, self._bias_i32, conv.stride, conv.padding,
-                                   self.rs_bit, self.output_bit,
-                                   c_real=conv.in_channels)      # Conv+RightShift+BiasAdd+Sp+DeQuan
+                                   self.rs_bit, self.output_bit, c_real=conv.in_channels,
+                                   dilation=getattr(self, "_dilation", (1, 1)))   # Conv+RightShift+BiasAdd+Sp+DeQuan
         return out
 
 

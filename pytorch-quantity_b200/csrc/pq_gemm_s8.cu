@@ -272,6 +272,7 @@ struct GemmParams {
     int C;                     // padded channels (bytes per pixel)
     int P, Q;                  // output height / width (im2col mode)
     int stride_h, stride_w, pad_h, pad_w;
+    int dil_h, dil_w;          // filter dilation (im2col mode): tap (r, s) reads pixel offset (r * dil_h, s * dil_w)
     int rs, ob;                // RightShift amount, output fractional bit
     int hw;                    // pixels per image for the fp32 NCHW store (1: plain [M][N])
     int relu;                  // int8 pipeline: apply max(y, 0) in the epilogue (a following nn.ReLU)
@@ -674,7 +675,8 @@ __device__ __forceinline__ void produce_a(const GemmParams &p, const CUtensorMap
                 if (MODE == 2)                 // filter row kb: padded input row = p * stride_h + kb
                     tma_load_5d_a(tmap_a, bar, dst, 0, wq, hp + kb / p.stride_h, kb % p.stride_h, nb);
                 else if (MODE == 1)
-                    tma_load_im2col_4d_a(tmap_a, bar, dst, cb * BK, w0, h0, nb, (uint16_t)s, (uint16_t)r);
+                    tma_load_im2col_4d_a(tmap_a, bar, dst, cb * BK, w0, h0, nb, (uint16_t)(s * p.dil_w),
+                                         (uint16_t)(r * p.dil_h));
                 else
                     tma_load_2d_a(tmap_a, bar, dst, kb * BK, m0);
             }
@@ -1011,12 +1013,12 @@ int encode_nd(CUtensorMap *map, const void *base, int rank, const cuuint64_t *di
     return r == CUDA_SUCCESS ? PQ_OK : PQ_EUNSUPPORTED;
 }
 
-int encode_im2col(CUtensorMap *map, const void *base, const pq_conv_desc &d, int bk)
+int encode_im2col(CUtensorMap *map, const void *base, const pq_conv_desc &d, int bk, int dil_h, int dil_w)
 {
     cuuint64_t dims[4] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
     cuuint64_t strides[3] = {(cuuint64_t)d.C, (cuuint64_t)d.W * d.C, (cuuint64_t)d.H * d.W * d.C};
     int lower[2] = {-d.pad_w, -d.pad_h};
-    int upper[2] = {d.pad_w - (d.S - 1), d.pad_h - (d.R - 1)};
+    int upper[2] = {d.pad_w - (d.S - 1) * dil_w, d.pad_h - (d.R - 1) * dil_h};
     cuuint32_t estr[4] = {1, (cuuint32_t)d.stride_w, (cuuint32_t)d.stride_h, 1};
     CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void *>(base), dims, strides,
                                  lower, upper, (cuuint32_t)bk, (cuuint32_t)pq::kBM, estr,
@@ -1195,7 +1197,16 @@ extern "C" int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const in
 
 namespace {
 int conv_impl(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q, const pq_conv_desc *desc_host,
-              int flags, float *out_f32_nchw, int8_t *out_s8_nhwc, const pq_add_desc *add, pq_stream_t stream);
+              int flags, float *out_f32_nchw, int8_t *out_s8_nhwc, const pq_add_desc *add, pq_stream_t stream,
+              int dil_h = 1, int dil_w = 1);
+}
+
+extern "C" int pq_conv2d_s8_dil(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
+                                const pq_conv_desc *desc_host, int dil_h, int dil_w, int flags, float *out_f32_nchw,
+                                int8_t *out_s8_nhwc, pq_stream_t stream)
+{
+    return conv_impl(x_nhwc, w_krsc, bias_q, desc_host, flags, out_f32_nchw, out_s8_nhwc, nullptr, stream, dil_h,
+                     dil_w);
 }
 
 extern "C" int pq_conv2d_s8_ex(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
@@ -1214,14 +1225,18 @@ extern "C" int pq_conv2d_s8_add(const int8_t *x_nhwc, const int8_t *w_krsc, cons
 
 namespace {
 int conv_impl(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q, const pq_conv_desc *desc_host,
-              int flags, float *out_f32_nchw, int8_t *out_s8_nhwc, const pq_add_desc *add, pq_stream_t stream)
+              int flags, float *out_f32_nchw, int8_t *out_s8_nhwc, const pq_add_desc *add, pq_stream_t stream,
+              int dil_h, int dil_w)
 {
     if (!x_nhwc || !w_krsc || !bias_q || !desc_host || (!out_f32_nchw && !out_s8_nhwc)) return PQ_EINVAL;
     const pq_conv_desc &d = *desc_host;
     if (d.N <= 0 || d.H <= 0 || d.W <= 0 || d.C <= 0 || d.K <= 0 || d.R <= 0 || d.S <= 0) return PQ_EINVAL;
-    if (d.stride_h <= 0 || d.stride_w <= 0 || d.pad_h < 0 || d.pad_w < 0) return PQ_EINVAL;
-    if (d.P != (d.H + 2 * d.pad_h - d.R) / d.stride_h + 1 || d.Q != (d.W + 2 * d.pad_w - d.S) / d.stride_w + 1)
+    if (d.stride_h <= 0 || d.stride_w <= 0 || d.pad_h < 0 || d.pad_w < 0 || dil_h <= 0 || dil_w <= 0) return PQ_EINVAL;
+    const int r_eff = (d.R - 1) * dil_h + 1, s_eff = (d.S - 1) * dil_w + 1;       // footprint of the dilated filter
+    if (d.H + 2 * d.pad_h < r_eff || d.W + 2 * d.pad_w < s_eff) return PQ_EINVAL;
+    if (d.P != (d.H + 2 * d.pad_h - r_eff) / d.stride_h + 1 || d.Q != (d.W + 2 * d.pad_w - s_eff) / d.stride_w + 1)
         return PQ_EINVAL;
+    if (r_eff > 255 || s_eff > 255) return PQ_EUNSUPPORTED;
     if ((d.C & 15) || (((uintptr_t)x_nhwc | (uintptr_t)w_krsc) & 15)) return PQ_EALIGN;
     if (d.ob < -100 || d.ob > 100 || d.rs > 24 || d.rs < -24 || d.stride_h > 8 || d.stride_w > 8) return PQ_EUNSUPPORTED;
     if ((uintptr_t)bias_q & 15) return PQ_EALIGN;
@@ -1237,13 +1252,14 @@ int conv_impl(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
     int bn = pick_bn(M, d.K);
     if (add && bn < 64) bn = 64;                 // the fused-add pass works on 64-column slabs
     CUtensorMap ta, tb;
-    if ((rc = encode_im2col(&ta, x_nhwc, d, bk)) != PQ_OK) return rc;
+    if ((rc = encode_im2col(&ta, x_nhwc, d, bk, dil_h, dil_w)) != PQ_OK) return rc;
     const uint64_t ktot = (uint64_t)d.R * d.S * d.C;
     if ((rc = encode_2d(&tb, w_krsc, ktot, d.K, ktot, bk, bn)) != PQ_OK) return rc;
     pq::GemmParams p = {};
     p.M = (int)M; p.N = d.K; p.a_im2col = 1;
     p.R = d.R; p.S = d.S; p.C = d.C; p.cblocks = d.C / bk; p.num_kb = d.R * d.S * p.cblocks;
     p.P = d.P; p.Q = d.Q; p.stride_h = d.stride_h; p.stride_w = d.stride_w; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
+    p.dil_h = dil_h; p.dil_w = dil_w;
     p.rs = d.rs; p.ob = d.ob; p.hw = d.P * d.Q; p.bias = bias_q; p.out_f32 = out_f32_nchw; p.out_s8 = out_s8_nhwc;
     p.relu = flags & PQ_FLAG_RELU;
     apply_bias_fold(p, bias_q, flags, d.K, d.rs);

@@ -11,16 +11,33 @@
 //   * the running tail `threshold_sum - distribution[threshold]` (:108) is a sequential chain
 //     computed once per tensor in kl_prepare_kernel.
 // Not bandwidth bound (16 KB of input per tensor); reported as microseconds per tensor.
+//
+// The bin count is the reference's INTERVAL_NUM (tools/configs.yml:23), a run-time value `nbins`; the kernels are
+// compiled for two capacities CAP (2048: the default and everything below; 8192 = PQ_HIST_BINS_MAX above) that
+// only size the per-thread register arrays and the leaf tables.  Shared memory is dynamic (16 * nbins bytes).
 #include "pq_common.cuh"
 
 namespace pq {
 
-constexpr int kBins = PQ_HIST_BINS;             // 2048
 constexpr int kTarget = PQ_KL_TARGET_BIN;       // 128
-constexpr int kCand = PQ_KL_CANDIDATES;         // 1920
 constexpr int kKlThreads = 256;
-constexpr int kPerThread = kBins / kKlThreads;  // 8 consecutive bins per thread
-constexpr int kWsP = 0, kWsTail = kBins, kWsKl = kBins + kCand, kWsDoubles = 6144;
+
+// workspace layout per tensor, in doubles: P[nbins] | tail[nbins - 128] | KL[nbins - 128]
+struct KlGeom {
+    int nbins, cand;            // cand = nbins - 128
+    int ws_tail, ws_kl, ws_doubles;
+};
+
+inline KlGeom kl_geom(int nbins)
+{
+    KlGeom g;
+    g.nbins = nbins;
+    g.cand = nbins - kTarget;
+    g.ws_tail = nbins;
+    g.ws_kl = nbins + g.cand;
+    g.ws_doubles = 3 * nbins;
+    return g;
+}
 
 // numpy pairwise_sum leaf: n <= 128
 __device__ __forceinline__ double np_leaf_sum(const double *a, int n)
@@ -45,7 +62,7 @@ __device__ __forceinline__ double np_leaf_sum(const double *a, int n)
 }
 
 // Leaves of numpy's recursion for a length-n vector, in left-to-right order.
-constexpr int kMaxLeaves = 64;
+constexpr int kMaxLeaves = 256;                 // n <= 8192: at most 8192 / 64 + a few leaves
 __device__ int np_build_leaves(int n, int *leaf_off, int *leaf_len)
 {
     int stack_off[16], stack_len[16], sp = 0, count = 0;
@@ -88,17 +105,19 @@ __device__ double np_block_sum(const double *a, int n, int *s_off, int *s_len, d
     return total;
 }
 
-// ---- per tensor: P = float32(counts) / (sum + 1e-12); tail[T] for T = 128..2047 ----------
+// ---- per tensor: P = float32(counts) / (sum + 1e-12); tail[T] for T = 128..nbins-1 ----------
 __global__ void __launch_bounds__(kKlThreads)
-kl_prepare_kernel(const double *__restrict__ counts, double *__restrict__ workspace)
+kl_prepare_kernel(const double *__restrict__ counts, double *__restrict__ workspace, const KlGeom geo)
 {
-    __shared__ double s_p[kBins];
+    extern __shared__ double s_dyn[];                      // [nbins]
+    double *s_p = s_dyn;
     __shared__ double s_red[kKlThreads / 32];
     __shared__ int s_off[kMaxLeaves], s_len[kMaxLeaves], s_cnt;
     __shared__ double s_sum[kMaxLeaves];
     __shared__ double s_total;
+    const int kBins = geo.nbins, kWsP = 0, kWsTail = geo.ws_tail;
     const double *c = counts + (size_t)blockIdx.x * kBins;
-    double *ws = workspace + (size_t)blockIdx.x * kWsDoubles;
+    double *ws = workspace + (size_t)blockIdx.x * geo.ws_doubles;
 
     // hist.sum(): integer-valued addends, exact in any order below 2^53
     double part = 0.0;
@@ -131,18 +150,22 @@ kl_prepare_kernel(const double *__restrict__ counts, double *__restrict__ worksp
 }
 
 // ---- per (candidate T, tensor): the divergence of quantizer.py:103-161 + :169-174 ----------
+template <int CAP>
 __global__ void __launch_bounds__(kKlThreads)
-kl_candidate_kernel(double *__restrict__ workspace, double *__restrict__ kl_out)
+kl_candidate_kernel(double *__restrict__ workspace, double *__restrict__ kl_out, const KlGeom geo)
 {
-    __shared__ double s_p[kBins];
-    __shared__ double s_term[kBins];
+    constexpr int kPerThread = CAP / kKlThreads;           // consecutive bins per thread (8 for CAP = 2048)
+    extern __shared__ double s_dyn[];                      // [nbins] P, [nbins] terms
+    double *s_p = s_dyn;
+    double *s_term = s_dyn + geo.nbins;
     __shared__ double s_ev[kTarget];
     __shared__ int s_warp_cnt[kKlThreads / 32];
     __shared__ int s_off[kMaxLeaves], s_len[kMaxLeaves], s_cnt;
     __shared__ double s_sum[kMaxLeaves];
+    const int kWsP = 0, kWsTail = geo.ws_tail, kWsKl = geo.ws_kl, kCand = geo.cand;
 
     const int T = kTarget + blockIdx.x;
-    double *ws = workspace + (size_t)blockIdx.y * kWsDoubles;
+    double *ws = workspace + (size_t)blockIdx.y * geo.ws_doubles;
     for (int i = threadIdx.x; i < T; i += kKlThreads) s_p[i] = ws[kWsP + i];
     const double tail = ws[kWsTail + blockIdx.x];
     const double npb = (double)T / (double)kTarget;                      // :112, exact dyadic
@@ -228,13 +251,14 @@ kl_candidate_kernel(double *__restrict__ workspace, double *__restrict__ kl_out)
     }
 }
 
-// ---- per tensor: first strict minimum below 66666, default 2047  (:99-101, :163-165) -------
+// ---- per tensor: first strict minimum below 66666, default nbins - 1  (:99-101, :163-165) -------
 __global__ void __launch_bounds__(kKlThreads)
-kl_argmin_kernel(const double *__restrict__ workspace, int *__restrict__ threshold)
+kl_argmin_kernel(const double *__restrict__ workspace, int *__restrict__ threshold, const KlGeom geo)
 {
     __shared__ double s_v[kKlThreads];
     __shared__ int s_i[kKlThreads];
-    const double *kl = workspace + (size_t)blockIdx.x * kWsDoubles + kWsKl;
+    const int kCand = geo.cand, kBins = geo.nbins;
+    const double *kl = workspace + (size_t)blockIdx.x * geo.ws_doubles + geo.ws_kl;
     double best = __longlong_as_double(0x7ff0000000000000LL);   // +inf
     int bi = kCand;
     for (int i = threadIdx.x; i < kCand; i += kKlThreads) {
@@ -259,17 +283,39 @@ kl_argmin_kernel(const double *__restrict__ workspace, int *__restrict__ thresho
 
 }  // namespace pq
 
-extern "C" size_t pq_kl_workspace_doubles(void) { return pq::kWsDoubles; }
+extern "C" size_t pq_kl_workspace_doubles(void) { return 3 * PQ_HIST_BINS; }
+
+extern "C" size_t pq_kl_workspace_doubles_n(int nbins) { return nbins > 0 ? (size_t)3 * nbins : 0; }
+
+extern "C" int pq_kl_search_n_f64(const double *counts, int k, int nbins, double *workspace, double *kl,
+                                  int *threshold, pq_stream_t stream)
+{
+    if (k == 0) return PQ_OK;
+    if (k < 0 || !counts || !workspace || !threshold) return PQ_EINVAL;
+    if (nbins <= PQ_KL_TARGET_BIN) return PQ_EINVAL;       // the reference's loop range(128, nbins) would be empty
+    if (k > 65535 || nbins > PQ_HIST_BINS_MAX) return PQ_EUNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    const pq::KlGeom geo = pq::kl_geom(nbins);
+    const size_t smem_p = (size_t)nbins * 8, smem_c = (size_t)nbins * 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PQ_CUDA_TRY(cudaFuncSetAttribute(pq::kl_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         PQ_HIST_BINS_MAX * 8));
+        PQ_CUDA_TRY(cudaFuncSetAttribute(pq::kl_candidate_kernel<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         PQ_HIST_BINS_MAX * 16));
+        attr_set = true;
+    }
+    pq::kl_prepare_kernel<<<k, pq::kKlThreads, smem_p, s>>>(counts, workspace, geo);
+    if (nbins <= 2048)
+        pq::kl_candidate_kernel<2048><<<dim3(geo.cand, k), pq::kKlThreads, smem_c, s>>>(workspace, kl, geo);
+    else
+        pq::kl_candidate_kernel<8192><<<dim3(geo.cand, k), pq::kKlThreads, smem_c, s>>>(workspace, kl, geo);
+    pq::kl_argmin_kernel<<<k, pq::kKlThreads, 0, s>>>(workspace, threshold, geo);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int pq_kl_search_f64(const double *counts, int k, double *workspace, double *kl,
                                 int *threshold, pq_stream_t stream)
 {
-    if (k == 0) return PQ_OK;
-    if (k < 0 || !counts || !workspace || !threshold) return PQ_EINVAL;
-    if (k > 65535) return PQ_EUNSUPPORTED;
-    cudaStream_t s = (cudaStream_t)stream;
-    pq::kl_prepare_kernel<<<k, pq::kKlThreads, 0, s>>>(counts, workspace);
-    pq::kl_candidate_kernel<<<dim3(pq::kCand, k), pq::kKlThreads, 0, s>>>(workspace, kl);
-    pq::kl_argmin_kernel<<<k, pq::kKlThreads, 0, s>>>(workspace, threshold);
-    return (int)cudaGetLastError();
+    return pq_kl_search_n_f64(counts, k, PQ_HIST_BINS, workspace, kl, threshold, stream);
 }

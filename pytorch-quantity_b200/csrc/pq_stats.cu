@@ -108,3 +108,30 @@ extern "C" int pq_hist2048_multi_f32(const float *const *xs_host, const uint64_t
         t, reinterpret_cast<unsigned long long *>(hist));
     return (int)cudaGetLastError();
 }
+
+extern "C" int pq_hist_multi_f32(const float *const *xs_host, const uint64_t *ns_host, const float *intervals_host,
+                                 int k, int nbins, long long *hist, pq_stream_t stream)
+{
+    if (nbins == PQ_HIST_BINS) return pq_hist2048_multi_f32(xs_host, ns_host, intervals_host, k, hist, stream);
+    if (nbins < 1) return PQ_EINVAL;
+    if (nbins > PQ_HIST_BINS_MAX) return PQ_EUNSUPPORTED;
+    if (k == 0) return PQ_OK;
+    if (!hist || !intervals_host) return PQ_EINVAL;
+    for (int i = 0; i < k; ++i)
+        if (!(intervals_host[i] > 0.0f)) return PQ_EINVAL;
+    pq::SegTable t;
+    int rc = build_table(t, xs_host, ns_host, intervals_host, k);
+    if (rc != PQ_OK) return rc;
+    const size_t smem = (size_t)nbins * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PQ_CUDA_TRY(cudaFuncSetAttribute(pq::hist_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         PQ_HIST_BINS_MAX * 4));
+        attr_set = true;
+    }
+    int ctas_per_sm = (int)((200 * 1024) / (smem + 1024));
+    ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 8 ? 8 : ctas_per_sm);
+    pq::hist_generic_kernel<<<grid_for(t.total_chunks, ctas_per_sm), pq::kStatThreads, smem, (cudaStream_t)stream>>>(
+        t, nbins, reinterpret_cast<unsigned long long *>(hist));
+    return (int)cudaGetLastError();
+}

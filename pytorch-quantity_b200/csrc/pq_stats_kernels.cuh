@@ -444,4 +444,70 @@ hist_multi_kernel(const __grid_constant__ SegTable tab, unsigned long long *__re
     }
 }
 
+// ------------------------------------------------------- histogram, any INTERVAL_NUM (configs.yml:23)
+// The reference's bin count is a configuration value (distribution_collector.py:52-63); 2048 is only its
+// default and is what hist_multi_kernel above is specialised for (exact reciprocal trick, 8 KB-aligned bins).
+// Any other count takes this reference-literal kernel: same chunking and multi-tensor table, one IEEE
+// division per element, `nbins` shared counters per CTA.  Still a streaming HBM kernel, ~0.6 of peak.
+__device__ __forceinline__ void hist_add_exact_n(unsigned int *sh, float v, float interval, int nbins)
+{
+    if (v != 0.0f) {
+        const float q = __fdiv_rn(fabsf(v), interval);
+        const int idx = q >= (float)(nbins - 1) ? nbins - 1 : (int)q;     // np.minimum(int32(q), nbins - 1)
+        atomicAdd(sh + idx, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(kStatThreads)
+hist_generic_kernel(const __grid_constant__ SegTable tab, int nbins, unsigned long long *__restrict__ hist)
+{
+    extern __shared__ unsigned int s_bins[];               // [nbins]
+    const unsigned int per = (tab.total_chunks + gridDim.x - 1) / gridDim.x;
+    unsigned int c = blockIdx.x * per;
+    const unsigned int c_end = min(c + per, tab.total_chunks);
+    if (c >= c_end) return;
+    for (int i = threadIdx.x; i < nbins; i += kStatThreads) s_bins[i] = 0;
+    __syncthreads();
+    int seg = seg_of_chunk(tab, c);
+    while (c < c_end) {
+        const SegGeom g = seg_geom(tab, seg);
+        const float interval = tab.param[seg];
+        const unsigned int seg_first = seg ? tab.chunk_end[seg - 1] : 0;
+        const unsigned int seg_last = min(tab.chunk_end[seg], c_end);
+        for (; c < seg_last; ++c) {
+            const unsigned long long v0 = (unsigned long long)(c - seg_first) * kChunkVecs;
+            const float4 *src = g.body + v0;
+            const unsigned long long left = g.nvec > v0 ? g.nvec - v0 : 0;
+            const unsigned int nv = left >= (unsigned long long)kChunkVecs ? (unsigned int)kChunkVecs : (unsigned int)left;
+            for (unsigned int i = threadIdx.x; i < nv; i += 4 * kStatThreads) {
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (i + j * kStatThreads < nv) v[j] = ld_stream_f4(src + i + j * kStatThreads);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (i + j * kStatThreads < nv) {
+                        hist_add_exact_n(s_bins, v[j].x, interval, nbins);
+                        hist_add_exact_n(s_bins, v[j].y, interval, nbins);
+                        hist_add_exact_n(s_bins, v[j].z, interval, nbins);
+                        hist_add_exact_n(s_bins, v[j].w, interval, nbins);
+                    }
+            }
+            if (c == seg_first) {
+                if (threadIdx.x < g.head) hist_add_exact_n(s_bins, g.p[threadIdx.x], interval, nbins);
+                if (threadIdx.x < g.tail) hist_add_exact_n(s_bins, g.p[g.n - g.tail + threadIdx.x], interval, nbins);
+            }
+        }
+        __syncthreads();
+        unsigned long long *out = hist + (size_t)seg * nbins;
+        for (int b = threadIdx.x; b < nbins; b += kStatThreads) {
+            const unsigned int cnt = s_bins[b];
+            s_bins[b] = 0;
+            if (cnt) atomicAdd(out + b, (unsigned long long)cnt);
+        }
+        __syncthreads();
+        ++seg;
+    }
+}
+
 }  // namespace pq

@@ -487,10 +487,12 @@ class Quantity(object):
             rewriter.rewrite_weight_dir(weight_bits, new_weight)
         self._log("Done!")
 
-    def weight_quantize(self):
+    def weight_quantize(self, write_json=True):
         """Per-parameter max-abs -> bit, int8 values -> JSON, weight.table (reference :592-677).
         The max-abs of all parameters is one multi-tensor kernel launch; rounding / clamping is
-        the fake-quant kernel without the dequantise step."""
+        the fake-quant kernel without the dequantise step.  ``write_json=False`` (not a reference option) writes
+        only weight.table -- all that Reconstruction needs -- and skips the per-parameter JSON files and the
+        rewriter pass over them, which are 100 % host serialisation time."""
         settings, out = self.config["SETTINGS"], self.config["OUTPUT"]
         names, shapes, flats = [], {}, []
         for name, param in self.model.named_parameters():
@@ -529,7 +531,7 @@ class Quantity(object):
             bit = bits_co[name]
             q = _native.fakequant(params[name], bit, -128.0, 127.0, dequant=False)   # around + clip
             table.append(name + " " + str(bit))
-            if self.rank != 0:
+            if self.rank != 0 or not write_json:
                 continue
             content = q.to(torch.int32).view(shapes[name]).cpu().numpy()
             if name.endswith("weight"):
@@ -543,7 +545,8 @@ class Quantity(object):
                 for line in table:
                     f.write(line + "\n")
         _barrier()
-        self.rewrite_weight()
+        if write_json:
+            self.rewrite_weight()
 
     def dilation_to_zero_padding(self, tensor, dilation):
         """Zero-stuff a dilated kernel (reference :679-693); dilation (2, 2) only."""

@@ -259,6 +259,51 @@ def gen_intsim():
     _save("intsim.npz", **out)
 
 
+# ----------------------------------------------------- intsim: dilation and groups
+# name, B, Cin, H, W, Cout, k, stride, pad, dilation, groups, bits(w, in, out), wscale, xscale
+INTSIM_EXT_CASES = [
+    ("dil2_3x3", 2, 32, 12, 12, 48, 3, 1, 2, 2, 1, (8, 5, 4), 0.4, 2.0),
+    ("dil2_3x3_s2", 2, 64, 13, 11, 32, 3, 2, 2, 2, 1, (8, 5, 4), 0.3, 2.0),
+    ("dil3_3x3_c16", 1, 16, 15, 15, 16, 3, 1, 3, 3, 1, (7, 4, 3), 0.8, 3.0),
+    ("dil2_smallc", 2, 3, 20, 20, 16, 3, 2, 2, 2, 1, (8, 5, 4), 0.45, 2.5),
+    ("groups2", 2, 64, 9, 9, 64, 3, 1, 1, 1, 2, (8, 5, 4), 0.4, 2.0),
+    ("groups4_1x1", 2, 64, 7, 7, 128, 1, 1, 0, 1, 4, (8, 5, 4), 0.4, 2.0),
+    ("groups8_cg4", 1, 32, 10, 10, 32, 3, 2, 1, 1, 8, (7, 5, 4), 0.6, 2.0),
+    ("depthwise", 1, 24, 8, 8, 24, 3, 1, 1, 1, 24, (7, 4, 3), 0.9, 3.0),
+    ("groups2_dil2", 1, 64, 11, 11, 32, 3, 1, 2, 2, 2, (8, 5, 4), 0.4, 2.0),
+]
+
+
+def intsim_ext_tensors(case):
+    name, B, Cin, H, W, Cout, k, stride, pad, dil, groups, bits, wscale, xscale = case
+    seed = 3000 + sum(ord(c) for c in name)
+    x = det_inputs.bell(B * Cin * H * W, seed, xscale).reshape(B, Cin, H, W)
+    w = det_inputs.bell(Cout * (Cin // groups) * k * k, seed + 1, wscale).reshape(Cout, Cin // groups, k, k)
+    b = det_inputs.bell(Cout, seed + 2, 4.0)
+    info = {"weight_bit": bits[0], "input_bit": bits[1], "output_bit": bits[2], "bias_bit": bits[2]}
+    return x, w, b, info
+
+
+def gen_intsim_ext():
+    """NewConv2d around dilated / grouped nn.Conv2d modules (the reference wraps any Conv2d,
+    new_quantity_op.py:104-133)."""
+    import torch
+    import torch.nn as nn
+    nq = ref_loader.load_l2("new_quantity_op")
+    out = {}
+    with torch.no_grad():
+        for case in INTSIM_EXT_CASES:
+            name, B, Cin, H, W, Cout, k, stride, pad, dil, groups = case[:11]
+            x, w, b, info = intsim_ext_tensors(case)
+            conv = nn.Conv2d(Cin, Cout, k, stride=stride, padding=pad, dilation=dil, groups=groups)
+            conv.weight.data.copy_(torch.from_numpy(w))
+            conv.bias.data.copy_(torch.from_numpy(b))
+            m = nq.NewConv2d(conv, dict(info))
+            out["conv/" + name + "/y"] = m(torch.from_numpy(x.copy())).numpy()
+            print(name, out["conv/" + name + "/y"].shape)
+    _save("intsim_ext.npz", **out)
+
+
 # ---------------------------------------------------------------- end-to-end runs
 def _read_workdir(test_dir):
     wd = os.path.join(test_dir, "workdir")
@@ -465,7 +510,51 @@ def gen_r18_224():
           % (res["seconds_activation_quantize"], res["seconds_weight_quantize"], wn))
 
 
-SECTIONS = {"stats": gen_stats, "kl": gen_kl, "fakequant": gen_fakequant, "intsim": gen_intsim,
+# ------------------------------------------------------------ INTERVAL_NUM != 2048
+BINS_CASES = (512, 1000, 4096)
+
+
+def bins_batches():
+    return [det_inputs.bell(60000, 71, 1.5), det_inputs.relu_bell(50000, 72, 3.0)]
+
+
+def gen_bins():
+    """INTERVAL_NUM is a configuration value (tools/configs.yml:23): the reference's collector and KL search
+    at 512, 1000 (not a power of two) and 4096 bins."""
+    dc = ref_loader.load_l2("distribution_collector")
+    qz = ref_loader.load_l2("quantizer")
+    out = {}
+    curves = {}
+
+    class Rec(qz.Quantizer):
+        def compute_kl_divergence(self, a, b):
+            v = qz.Quantizer.compute_kl_divergence(self, a, b)
+            curves.setdefault(self._cur, []).append(float(v))
+            return v
+
+    for nbins in BINS_CASES:
+        name = "t%d" % nbins
+        col = dc.DistributionCollector([name], interval_num=nbins, statistic=1, worker_num=1)
+        for b in bins_batches():
+            col.refresh_max_val({name: b})
+        iv = col.distribution_intervals[name]
+        for b in bins_batches():
+            col.add_to_distributions({name: b})
+        hist = col.distributions[name].copy()
+        r = Rec([name])
+        r._cur = name
+        _, bits, thr = r.quantize_worker([name], {name: hist}, {name: iv})
+        out[name + "/max"], _ = _scalar_record(col.max_vals[name])
+        out[name + "/interval"], _ = _scalar_record(iv)
+        out[name + "/hist"] = hist
+        out[name + "/kl"] = np.array(curves[name], dtype=np.float64)
+        out[name + "/bit"] = np.array([bits[0]], dtype=np.int64)
+        out[name + "/threshold_value"], _ = _scalar_record(thr[0])
+        print("bins", nbins, "bit", bits[0], "thr", thr[0], len(curves[name]))
+    _save("bins.npz", **out)
+
+
+SECTIONS = {"bins": gen_bins, "intsim_ext": gen_intsim_ext, "stats": gen_stats, "kl": gen_kl, "fakequant": gen_fakequant, "intsim": gen_intsim,
             "tiny": gen_tiny, "tiny_dkl": gen_tiny_dkl, "lenet": gen_lenet, "r18_224": gen_r18_224}
 
 if __name__ == "__main__":

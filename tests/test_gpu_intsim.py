@@ -241,3 +241,35 @@ def test_accumulator_range_debug_check():
     assert float(y.max()) == 127.0                                 # the int32 path itself stays exact and saturates
     model = nn.Sequential(m, small)
     assert set(nq.accumulator_report(model)) == {"0", "1"}
+
+
+# dilated and grouped convolutions: the reference wraps ANY nn.Conv2d (new_quantity_op.py:104-133)
+@pytest.mark.parametrize("case", gg.INTSIM_EXT_CASES, ids=[c[0] for c in gg.INTSIM_EXT_CASES])
+@pytest.mark.parametrize("pipeline", [False, True])
+def test_newconv2d_dilation_and_groups_vs_golden(oracle, case, pipeline):
+    """Dilation = im2col-TMA tap offsets (pq_conv2d_s8_dil), groups = one tensor-core convolution per group; against
+    the reference's NewConv2d around the same dilated / grouped nn.Conv2d (intsim_ext.npz) and the oracle."""
+    import common.quantity as cq
+    g = load_golden("intsim_ext.npz")
+    name, B, Cin, H, W, Cout, k, stride, pad, dil, groups = case[:11]
+    x, w, b, info = gg.intsim_ext_tensors(case)
+    conv = nn.Conv2d(Cin, Cout, k, stride=stride, padding=pad, dilation=dil, groups=groups)
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(w)); conv.bias.copy_(torch.from_numpy(b))
+        m = cq.NewConv2d(conv.cuda(), dict(info))
+        m.int8_pipeline = pipeline
+        y = m(dev(x))
+        if pipeline and hasattr(y, "dequantize"):
+            y = y.dequantize()
+    want = g["conv/" + name + "/y"]
+    assert y.shape == want.shape
+    assert np.array_equal(y.cpu().numpy(), want)
+    ref, _ = oracle.int_conv_layer(x, w, b, info, stride=stride, padding=pad, dilation=dil, groups=groups)
+    assert np.array_equal(ref, want)
+
+
+def test_newconv2d_unsupported_padding_mode_is_a_named_error():
+    import common.quantity as cq
+    conv = nn.Conv2d(16, 16, 3, padding=1, padding_mode="reflect").cuda()
+    with pytest.raises(NotImplementedError, match="PQ_EUNSUPPORTED"):
+        cq.NewConv2d(conv, {"weight_bit": 7, "input_bit": 4, "output_bit": 3, "bias_bit": 3})

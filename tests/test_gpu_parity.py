@@ -346,3 +346,45 @@ def test_collector_channel_max_extension(cq, oracle):
             want = oracle.absmax_per_channel(b[n].cpu().numpy(), 1, cur=want)
         assert np.array_equal(got[n], want)
         assert np.float32(got[n].max()) == dc.max_vals[n]             # consistent with the per-tensor reduction
+
+
+# ------------------------------------------------------------------ INTERVAL_NUM != 2048 (tools/configs.yml:23)
+@pytest.mark.parametrize("nbins", [512, 1000, 4096])
+def test_other_interval_num_vs_golden(nbins):
+    """DistributionCollector(interval_num=...) + Quantizer on the GPU at the reference's other bin counts: generic
+    histogram kernel (pq_hist_multi_f32) and run-time-sized KL search (pq_kl_search_n_f64) against the unmodified
+    reference's outputs (bins.npz)."""
+    import common.quantity as cq
+    from golden import gen_golden as gg
+    g = load_golden("bins.npz")
+    name = "t%d" % nbins
+    batches = [torch.from_numpy(b).cuda() for b in gg.bins_batches()]
+    col = cq.DistributionCollector([name], interval_num=nbins)
+    for b in batches:
+        col.refresh_max_val({name: b})
+    assert float(col.max_vals[name]) == float(g[name + "/max"][0])
+    iv = col.distribution_intervals[name]
+    assert float(iv) == float(g[name + "/interval"][0])
+    for b in batches:
+        col.add_to_distributions({name: b})
+    h = col.distributions[name]
+    assert h.shape == (nbins,) and np.array_equal(h, g[name + "/hist"])
+    qz = cq.Quantizer([name], keep_curves=True)
+    qz.quantize(col.distributions, col.distribution_intervals)
+    assert qz.bits[name] == int(g[name + "/bit"][0])
+    assert float(qz.threshold_value[name]) == float(g[name + "/threshold_value"][0])
+    np.testing.assert_allclose(qz.kl_curves.cpu().numpy()[0], g[name + "/kl"], rtol=1e-9, atol=1e-300)
+
+
+def test_interval_num_limits():
+    import common.quantity as cq
+    from common.quantity import _native
+    with pytest.raises(ValueError, match="INTERVAL_NUM"):
+        cq.DistributionCollector(["t"], interval_num=8193)
+    lib = _native.lib()
+    c = torch.zeros((1, 128), dtype=torch.float64, device="cuda")
+    ws = torch.zeros(4096, dtype=torch.float64, device="cuda")
+    thr = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert lib.pq_kl_search_n_f64(c.data_ptr(), 1, 128, ws.data_ptr(), None, thr.data_ptr(), None) == -1    # PQ_EINVAL
+    assert lib.pq_kl_search_n_f64(c.data_ptr(), 1, 8193, ws.data_ptr(), None, thr.data_ptr(), None) == -2   # PQ_EUNSUPPORTED
+    assert lib.pq_hist_multi_f32(None, None, None, 0, 9000, None, None) == -2

@@ -369,3 +369,27 @@ def test_c1_resnet18_reference_histograms(oracle):
         bit, thr, _t = oracle.quantize_distribution(g["dist/" + n], interv)
         assert float(thr) == j["thresholds"][n], n
         assert bit == j["raw_bits"][n], n
+
+
+# ------------------------------------------------------------------ INTERVAL_NUM != 2048 (tools/configs.yml:23)
+@pytest.mark.parametrize("nbins", [512, 1000, 4096])
+def test_other_interval_num_vs_golden(oracle, nbins):
+    """The oracle's collector / KL restatement at the reference's other bin counts (bins.npz: the unmodified
+    reference with interval_num = 512, 1000, 4096)."""
+    from golden import gen_golden as gg
+    g = load_golden("bins.npz")
+    name = "t%d" % nbins
+    batches = gg.bins_batches()
+    m = 0
+    for b in batches:
+        m = oracle.absmax_update(m, b)
+    assert float(m) == float(g[name + "/max"][0])
+    iv = oracle.interval(m, 1, nbins)
+    assert float(iv) == float(g[name + "/interval"][0]) and type(iv).__name__ == "float32"
+    h = sum(oracle.hist(b, iv, nbins) for b in batches)
+    assert np.array_equal(h, g[name + "/hist"])
+    t, kl = oracle.kl_search(oracle.normalize(h))
+    assert kl.shape == g[name + "/kl"].shape == (nbins - 128,)
+    np.testing.assert_allclose(kl, g[name + "/kl"], rtol=1e-12, atol=0)
+    bit, thr = oracle.threshold_to_bit(t, iv)
+    assert bit == int(g[name + "/bit"][0]) and float(thr) == float(g[name + "/threshold_value"][0])
