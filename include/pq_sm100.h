@@ -263,6 +263,10 @@ int pq_gemm_s8_add(const int8_t *a, const int8_t *w, const int32_t *bias_q, int 
                    const pq_add_desc *add_host, pq_stream_t stream);
 int pq_conv2d_s8_add(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
                      const pq_conv_desc *desc_host, const pq_add_desc *add_host, pq_stream_t stream);
+/* the same with flags: PQ_FLAG_BIAS_FOLDED (bias_q as written by pq_bias_fold_s32); PQ_FLAG_RELU is rejected
+ * (the ReLU of a fused add is add_host->out_relu). */
+int pq_conv2d_s8_add_ex(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
+                        const pq_conv_desc *desc_host, const pq_add_desc *add_host, int flags, pq_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,7 @@ SYMBOLS = {
     "pq_conv2d_s8_dil": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pq_gemm_s8_add": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pq_conv2d_s8_add": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "pq_conv2d_s8_add_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pq_relu_s8": (_i, [_vp, _vp, _sz, _vp]),
     "pq_maxpool_nhwc_s8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "pq_add_requant": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _sz, _vp, _vp, _i, _vp]),
@@ -419,8 +420,9 @@ def conv2d_s8_add(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, shortcut, sho
                   1 if shortcut_relu else 0, 1 if out_relu else 0, int(q_bit),
                   out16.data_ptr() if want16 else None, out8.data_ptr())
     with _Timed("conv_add_s8", 1, 2 * N * P * Q * K * R * S * (c_real or C), x_nhwc.device):        # int8 ops
-        check(lib().pq_conv2d_s8_add(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
-                                     ctypes.byref(add), _stream(x_nhwc)), "pq_conv2d_s8_add")
+        check(lib().pq_conv2d_s8_add_ex(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
+                                        ctypes.byref(add), _bias_flags(bias_q, K, False), _stream(x_nhwc)),
+              "pq_conv2d_s8_add_ex")
     return out16, out8
 
 

@@ -26,10 +26,12 @@ import torch.nn.functional as F
 from . import _native
 
 
-# NewConv2d + NewAdd (+ ReLU) in one kernel (pq_conv2d_s8_add).  Bit-identical, but on B200 the fused
-# epilogue is instruction-bound and currently slower than the HBM-bound pq_add_requant_ex it replaces
-# (ResNet-50 batch 512: 5.5 ms vs 1.3 + 2.5 ms), so it is off by default; see DESIGN.md section 4.
-FUSE_ADD_INTO_CONV = False
+# NewConv2d + NewAdd (+ ReLU) in one kernel (pq_conv2d_s8_add_ex): the convolution's int8 result never touches
+# memory.  Bit-identical to conv followed by pq_add_requant_ex; on ResNet-50 batch 512 the 16 fused launches take
+# 3.02 ms against 1.19 + 2.52 ms for the separate kernels (forward 6.83 -> 6.19 ms), so it is on by default.
+# PQ_FUSE_ADD=0 switches it off (A/B measurements).
+import os as _os
+FUSE_ADD_INTO_CONV = _os.environ.get("PQ_FUSE_ADD", "1") != "0"
 
 _METADATA = {"__get__", "size", "dim", "numel", "element_size", "ndimension", "is_floating_point", "__len__",
              "get_device", "is_complex", "nelement"}

@@ -344,13 +344,21 @@ template <int BN, bool FAST = true> struct EpiCfg {
     static_assert(!FAST || kSlab >= 32, "staged rows of >= 32 bytes");
 };
 
-template <int BN, int BK, int STAGES>
+// fused NewAdd epilogue (ADDK kernels): per epilogue warp one int8 output slab [32 rows][32 B] and two buffers
+// [32 rows][64 B] that receive the shortcut slab by TMA and are overwritten in place with the int16 sum
+constexpr int kAddSlab = 32;                                   // output channels per staged slab
+constexpr int kAddO8Bytes = 32 * kAddSlab;                     // 1 KB
+constexpr int kAddS16Bytes = 32 * kAddSlab * 2;                // 2 KB
+constexpr int kAddWarpBytes = kAddO8Bytes + 2 * kAddS16Bytes;  // 5 KB
+
+template <int BN, int BK, int STAGES, bool ADDK = false>
 struct GemmSmem {
     static constexpr int kABytes = kBM * BK;
     static constexpr int kBBytes = BN * BK;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kOutBytes = kEpiWarps * EpiCfg<BN, true>::kSlabBytes;   // warp-private int8 staging slabs (FAST is the larger)
-    static constexpr size_t kTotal = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + kOutBytes + 256 /*barriers*/;
+    static constexpr int kOutBytes = ADDK ? kEpiWarps * kAddWarpBytes
+                                          : kEpiWarps * EpiCfg<BN, true>::kSlabBytes;   // warp-private int8 staging slabs (FAST is the larger)
+    static constexpr size_t kTotal = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + kOutBytes + 512 /*barriers*/;
 };
 
 
@@ -388,8 +396,8 @@ __device__ __forceinline__ int requant_folded(int acc, int sh, int a_lo, int a_h
     return RELU ? max(t, 0) : t;
 }
 
-// FOLD: 0 = classic chain, 1 = folded bias, 2 = folded bias + fused ReLU (FAST, non-ADD, POS only)
-template <int BN, bool POS, bool FAST, bool ADD = false, int FOLD = 0>
+// FOLD: 0 = classic chain, 1 = folded bias, 2 = folded bias + fused ReLU (FAST, POS only)
+template <int BN, bool POS, bool FAST, int FOLD = 0>
 __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap *tmap_o, uint8_t *smem_o,
                                          uint64_t *tmem_full_bar, uint64_t *tmem_empty_bar, uint32_t tmem_base,
                                          int total_tiles, int n_tiles)
@@ -545,65 +553,6 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
                     *reinterpret_cast<uint4 *>(stage_buf + (o ^ (((o >> 7) & kSwzMask) << 4))) =
                         make_uint4(packed[j][0], packed[j][1], packed[j][2], packed[j][3]);
                 }
-                if (ADD) {
-                    // ---- fused NewAdd: second pass over the staged int8 slab with a transposed mapping -- 8
-                    // lanes per row, 8 columns per lane -- so that the shortcut is read and the int16 sum is
-                    // written with fully coalesced 128-byte row segments; the int8 result replaces y in place.
-                    __syncwarp();
-                    const int u = lane & 7, r4 = lane >> 3;
-                    const int cmul = 1 << p.add_cshift, smul = 1 << p.add_sshift;
-                    const int d = p.add_qshift < 0 ? -p.add_qshift : 0, rc = d ? (1 << (d - 1)) - 1 : 0;
-                    const bool col_ok = colb + 8 * u < p.N;
-#pragma unroll 2
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 4 * i + r4;
-                        const int gm = m0 + quad * 32 + r;
-                        const uint32_t o = (uint32_t)(r * kSlab + 8 * u);
-                        uint2 *yp = reinterpret_cast<uint2 *>(stage_buf + (o ^ (((o >> 7) & kSwzMask) << 4)));
-                        if (!(col_ok && gm < p.M)) continue;
-                        const size_t e = (size_t)gm * p.N + colb + 8 * u;
-                        int sc[8];
-                        if (p.add_is16) {
-                            const uint4 w = ldg_nc_u4(reinterpret_cast<const int16_t *>(p.add_sc) + e);
-                            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) { sc[2 * j] = prmt_sx(ww[j], 0x9910u); sc[2 * j + 1] = prmt_sx(ww[j], 0xbb32u); }
-                        } else {
-                            const uint2 w = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const int8_t *>(p.add_sc) + e));
-                            const uint32_t ww[2] = {w.x, w.y};
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                sc[4 * j] = prmt_sx(ww[j], 0x8880u); sc[4 * j + 1] = prmt_sx(ww[j], 0x9991u);
-                                sc[4 * j + 2] = prmt_sx(ww[j], 0xaaa2u); sc[4 * j + 3] = prmt_sx(ww[j], 0xbbb3u);
-                            }
-                        }
-                        const uint2 yb = *yp;
-                        const uint32_t yw[2] = {yb.x, yb.y};
-                        int num[8];
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            num[4 * j] = prmt_sx(yw[j], 0x8880u); num[4 * j + 1] = prmt_sx(yw[j], 0x9991u);
-                            num[4 * j + 2] = prmt_sx(yw[j], 0xaaa2u); num[4 * j + 3] = prmt_sx(yw[j], 0xbbb3u);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int sv = p.add_sc_relu ? max(sc[j], 0) : sc[j];
-                            num[j] = max(p.add_lo, min(p.add_hi, num[j] * cmul + sv * smul));
-                        }
-                        if (p.out16)
-                            *reinterpret_cast<uint4 *>(p.out16 + e) =
-                                make_uint4(__byte_perm((uint32_t)num[0], (uint32_t)num[1], 0x5410), __byte_perm((uint32_t)num[2], (uint32_t)num[3], 0x5410),
-                                           __byte_perm((uint32_t)num[4], (uint32_t)num[5], 0x5410), __byte_perm((uint32_t)num[6], (uint32_t)num[7], 0x5410));
-                        if (d) {                       // ties to even; the pack saturates
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) num[j] = (num[j] + rc + ((num[j] >> d) & 1)) >> d;
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) num[j] = max(-128, min(127, num[j])) << p.add_qshift;
-                        }
-                        *yp = make_uint2(pack4_sat_s8(num[0], num[1], num[2], num[3]), pack4_sat_s8(num[4], num[5], num[6], num[7]));
-                    }
-                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
@@ -619,6 +568,253 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
         }
     }
     if (staged && lane == 0) bulk_wait_read0();
+}
+
+
+// ------------------------------------------------------------------- fused NewConv2d + NewAdd epilogue
+// NewAdd (new_quantity_op.py:166-174) and the nn.ReLU after it, evaluated on the accumulators of the producing
+// convolution while they are still in registers, in the SAME lane-owns-row mapping as the TMEM load (lane =
+// output pixel, 16 consecutive channels per chunk):
+//   y    = RightShift / BiasAdd / Sp of the accumulator (int8 range, bit ob)              32-bit, as above
+//   sum  = clamp(y * 2^cshift + shortcut * 2^sshift, lo, hi)   at bit o = max(ob, shortcut bit)   packed s16x2
+//   out16 = sum (the exact Eltwise output, for the next identity shortcut)
+//   out8  = Quantity(q_bit)(sum)  (ties-to-even shift, saturated; what the next convolution reads)
+// The shortcut slab [32 rows][32 channels] of the warp arrives by TMA one slab AHEAD (two buffers per warp, own
+// mbarriers) into swizzled shared memory, the lane reads its own row from there (conflict-free LDS.128), the
+// int16 sum overwrites the shortcut in place and leaves by a second TMA store next to the int8 slab.  No lane
+// ever touches global memory, every global transaction is a full 64-byte / 32-byte row segment, and the
+// arithmetic after the shift runs on packed 16-bit pairs (VIADDMNMX.S16x2, VIMNMX.S16x2): ~7 ALU operations per
+// element instead of the 27 of the former second pass over the staged slab.
+__device__ __forceinline__ uint32_t pack2_sat_s16(int hi, int lo)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return d;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int BN, bool POS, bool FOLD>
+__device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensorMap *tmap_o, const CUtensorMap *tmap_sc,
+                                             const CUtensorMap *tmap_o16, uint8_t *smem_o, uint64_t *sc_bar_all,
+                                             uint64_t *tmem_full_bar, uint64_t *tmem_empty_bar, uint32_t tmem_base,
+                                             int total_tiles, int n_tiles)
+{
+    using E = EpiCfg<BN, true>;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int quad = warp & 3;
+    const int idx = (warp - 2) >> 2;
+    const int group = idx / E::kColSplit;
+    const int part = idx % E::kColSplit;
+    constexpr int kCols = E::kCols, kSlabs = kCols / kAddSlab;
+    const uint32_t wbase = smem_u32(smem_o + (warp - 2) * kAddWarpBytes);
+    const uint32_t o8_base = wbase, s16_base = wbase + kAddO8Bytes;
+    const uint32_t bar_base = smem_u32(sc_bar_all + 2 * (warp - 2));
+    const Requant rq = make_requant(p.rs, 0);
+    const bool sc16 = p.add_is16 != 0;
+    const uint32_t sc_bytes = sc16 ? (uint32_t)kAddS16Bytes : (uint32_t)kAddO8Bytes;
+    // constants of the packed arithmetic
+    const int cmul = 1 << p.add_cshift;
+    const uint32_t y_hi2 = (uint32_t)(127 * cmul) * 0x10001u, y_lo2 = ((uint32_t)(-128 * cmul) & 0xffffu) * 0x10001u;
+    const uint32_t s_hi2 = (uint32_t)p.add_hi * 0x10001u, s_lo2 = ((uint32_t)p.add_lo & 0xffffu) * 0x10001u;
+    const bool out_relu = p.add_lo == 0;
+    const int d = p.add_qshift < 0 ? -p.add_qshift : 0, rc = d ? (1 << (d - 1)) - 1 : 0;
+    const int a_hi = 127 * (1 << rq.sh) + rq.half - 1, a_lo = -128 * (1 << rq.sh) - rq.half + 1;
+    // swizzled shared-memory offsets of this lane's row: 64-byte rows (int16) and 32-byte rows (int8)
+    auto off16 = [&](int chunk16) { return (uint32_t)(lane * 64 + ((chunk16 ^ ((lane >> 1) & 3)) << 4)); };
+    auto off8 = [&](int chunk16) { return (uint32_t)(lane * 32 + ((chunk16 ^ ((lane >> 2) & 1)) << 4)); };
+
+    // this warp's tiles: it = group, group + kGroups, ...; a tile counts only if its first column is inside N
+    auto tile_of = [&](int it) { return blockIdx.x + it * (int)gridDim.x; };
+    auto n0_of = [&](int tile) { return (n_tiles == 1 ? 0 : tile % n_tiles) * BN + part * kCols; };
+    auto next_loaded_it = [&](int it) {              // first it' >= it whose tile exists and has columns for this warp
+        for (;; it += E::kGroups) {
+            const int t = tile_of(it);
+            if (t >= total_tiles) return -1;
+            if (n0_of(t) < p.N) return it;
+        }
+    };
+    auto issue_load = [&](int buf, int tile, int slab) {     // leader lane only
+        const int m0r = (tile / n_tiles) * kBM + quad * 32, colb = n0_of(tile) + slab * kAddSlab;
+        const uint32_t bar = bar_base + 8u * (uint32_t)buf;
+        mbar_expect_tx_a(bar, sc_bytes);
+        tma_load_2d_a(tmap_sc, bar, s16_base + (uint32_t)buf * kAddS16Bytes, sc16 ? colb * 2 : colb, m0r);
+    };
+
+    uint32_t ph0 = 0u, ph1 = 0u;                       // parity of the next completion of either buffer's barrier
+    int cur = 0;                                       // buffer that holds (or will hold) the current slab's shortcut
+    {
+        const int it0 = next_loaded_it(group);
+        if (it0 >= 0 && lane == 0) issue_load(0, tile_of(it0), 0);
+    }
+    for (int it = group;; it += E::kGroups) {
+        const int tile = tile_of(it);
+        if (tile >= total_tiles) break;
+        const int acc = it & (E::kAcc - 1);
+        const uint32_t acc_phase = (uint32_t)(it / E::kAcc) & 1u;
+        const int m0r = (tile / n_tiles) * kBM + quad * 32, n0 = n0_of(tile);
+        int nslab = (p.N - n0 + kAddSlab - 1) / kAddSlab;             // slabs of this warp inside N
+        nslab = nslab < 0 ? 0 : (nslab > kSlabs ? kSlabs : nslab);
+        mbar_wait(tmem_full_bar + acc, acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kCols);
+        if (nslab == 0) {                              // nothing to do here, but the accumulator must be released
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+            continue;
+        }
+        uint32_t a0[16], a1[16];
+        tmem_ld16(taddr, a0);
+#pragma unroll 1
+        for (int slab = 0; slab < nslab; ++slab) {
+            const int colb = n0 + slab * kAddSlab;
+            uint32_t pk[2][8];                         // conv result of the slab's two chunks as packed s16x2, x 2^cshift
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int ch = slab * 2 + j;
+                tmem_ld_wait();
+                if (ch + 1 < nslab * 2) {
+                    if (j & 1) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), a0);
+                    else tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), a1);
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+                }
+                const uint32_t (&a)[16] = (j & 1) ? a1 : a0;
+                if (colb + 16 * j < p.N) {
+                    int y[16];
+                    if (FOLD) {
+                        const int4 *cp = reinterpret_cast<const int4 *>(p.bias_c + colb + 16 * j);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int4 c4 = __ldg(cp + q);
+                            y[4 * q] = requant_folded<false>((int)a[4 * q], rq.sh, a_lo, a_hi, c4.x);
+                            y[4 * q + 1] = requant_folded<false>((int)a[4 * q + 1], rq.sh, a_lo, a_hi, c4.y);
+                            y[4 * q + 2] = requant_folded<false>((int)a[4 * q + 2], rq.sh, a_lo, a_hi, c4.z);
+                            y[4 * q + 3] = requant_folded<false>((int)a[4 * q + 3], rq.sh, a_lo, a_hi, c4.w);
+                        }
+                    } else {
+                        const int4 *bp = reinterpret_cast<const int4 *>(p.bias + colb + 16 * j);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int4 b4 = __ldg(bp + q);
+                            y[4 * q] = requant_t<POS>((int)a[4 * q], rq, b4.x);
+                            y[4 * q + 1] = requant_t<POS>((int)a[4 * q + 1], rq, b4.y);
+                            y[4 * q + 2] = requant_t<POS>((int)a[4 * q + 2], rq, b4.z);
+                            y[4 * q + 3] = requant_t<POS>((int)a[4 * q + 3], rq, b4.w);
+                        }
+                    }
+                    // (r + b) is within [-256, 254]: scale, pack, then the second saturation on the packed pairs
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t w = pack2_sat_s16(y[2 * q + 1] * cmul, y[2 * q] * cmul);
+                        pk[j][q] = __vmaxs2(__vmins2(w, y_hi2), y_lo2);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) pk[j][q] = 0u;
+                }
+            }
+            // ---- the shortcut of this slab has been on its way since the previous slab
+            const uint32_t sbuf = s16_base + (uint32_t)cur * kAddS16Bytes;
+            mbar_wait(sc_bar_all + 2 * (warp - 2) + cur, cur ? ph1 : ph0);
+            if (cur) ph1 ^= 1u; else ph0 ^= 1u;
+            uint32_t sc[2][8];
+            if (sc16) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint4 lo = lds_u4(sbuf + off16(2 * j)), hi = lds_u4(sbuf + off16(2 * j + 1));
+                    sc[j][0] = lo.x; sc[j][1] = lo.y; sc[j][2] = lo.z; sc[j][3] = lo.w;
+                    sc[j][4] = hi.x; sc[j][5] = hi.y; sc[j][6] = hi.z; sc[j][7] = hi.w;
+                }
+            } else {                                   // int8 shortcut: sign-extend byte pairs to s16x2
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint4 v = lds_u4(sbuf + off8(j));
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        sc[j][2 * q] = (uint32_t)prmt_sx(w[q], 0x9180u);
+                        sc[j][2 * q + 1] = (uint32_t)prmt_sx(w[q], 0xb3a2u);
+                    }
+                }
+            }
+            // every lane has its shortcut in registers: the buffers may now be rewritten.  The stores of the previous
+            // slab must have finished READING the int8 slab and the other int16 buffer before either is reused.
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            {                                          // prefetch the next slab's shortcut into the other buffer
+                int nt = tile, ns = slab + 1;
+                if (ns == nslab) {
+                    const int itn = next_loaded_it(it + E::kGroups);
+                    nt = itn < 0 ? -1 : tile_of(itn);
+                    ns = 0;
+                }
+                if (nt >= 0 && lane == 0) issue_load(cur ^ 1, nt, ns);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (colb + 16 * j >= p.N) continue;
+                uint32_t sum[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t sv = sc[j][q];
+                    if (p.add_sc_relu) sv = __vmaxs2(sv, 0u);
+                    if (p.add_sshift) {                // rare: shortcut at a coarser bit than the sum
+                        const int lo16 = (int)(short)(sv & 0xffffu), hi16 = (int)sv >> 16;
+                        sv = pack2_sat_s16(hi16 << p.add_sshift, lo16 << p.add_sshift);
+                    }
+                    sum[q] = out_relu ? __viaddmin_s16x2_relu(pk[j][q], sv, s_hi2)
+                                      : __vmaxs2(__viaddmin_s16x2(pk[j][q], sv, s_hi2), s_lo2);
+                }
+                if (p.out16) {
+                    sts_u4(sbuf + off16(2 * j), sum[0], sum[1], sum[2], sum[3]);
+                    sts_u4(sbuf + off16(2 * j + 1), sum[4], sum[5], sum[6], sum[7]);
+                }
+                uint32_t o[4];
+                if (p.add_qshift == 0) {               // same bit: saturate the pairs, keep the low bytes
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t w0 = __vmins2(sum[2 * q], 0x007f007fu), w1 = __vmins2(sum[2 * q + 1], 0x007f007fu);
+                        if (!out_relu) { w0 = __vmaxs2(w0, 0xff80ff80u); w1 = __vmaxs2(w1, 0xff80ff80u); }
+                        o[q] = __byte_perm(w0, w1, 0x6420);
+                    }
+                } else {                               // general requantisation in 32 bits (ties to even / left shift)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        int e[4] = {(int)(short)(sum[2 * q] & 0xffffu), (int)sum[2 * q] >> 16,
+                                    (int)(short)(sum[2 * q + 1] & 0xffffu), (int)sum[2 * q + 1] >> 16};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            e[u] = d ? (e[u] + rc + ((e[u] >> d) & 1)) >> d : max(-128, min(127, e[u])) << p.add_qshift;
+                        o[q] = pack4_sat_s8(e[0], e[1], e[2], e[3]);
+                    }
+                }
+                sts_u4(o8_base + off8(j), o[0], o[1], o[2], o[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(tmap_o, reinterpret_cast<const void *>(smem_o + (warp - 2) * kAddWarpBytes), colb, m0r);
+                if (p.out16)
+                    tma_store_2d(tmap_o16, reinterpret_cast<const void *>(smem_o + (warp - 2) * kAddWarpBytes + kAddO8Bytes +
+                                                                          cur * kAddS16Bytes), colb * 2, m0r);
+                bulk_commit();
+            }
+            cur ^= 1;
+        }
+    }
+    if (lane == 0) bulk_wait_read0();
 }
 
 // A-operand producer loop, specialised per addressing mode (0: 2-D [M][K] tiles, 1: im2col over NHWC,
@@ -686,12 +882,13 @@ __device__ __forceinline__ void produce_a(const GemmParams &p, const CUtensorMap
     }
 }
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, bool ADDK = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)     // 19 warps = 5 on one SM sub-partition: <= 104 registers / thread
 gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_o, const GemmParams p)
+               const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_sc,
+               const __grid_constant__ CUtensorMap tmap_o16, const GemmParams p)
 {
-    using Cfg = GemmSmem<BN, BK, STAGES>;
+    using Cfg = GemmSmem<BN, BK, STAGES, ADDK>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_a = smem;
@@ -702,7 +899,8 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t *tmem_full_bar = empty_bar + STAGES;      // [kAcc]
     uint64_t *tmem_empty_bar = tmem_full_bar + 4;      // [kAcc]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 4);
-    const bool fast_epi = p.stage_s8 && !p.out_f32;                    // which epilogue configuration runs
+    uint64_t *sc_bar = tmem_empty_bar + 5;             // [kEpiWarps][2] shortcut-slab barriers (ADDK kernels only)
+    const bool fast_epi = ADDK || (p.stage_s8 && !p.out_f32);          // which epilogue configuration runs
     const int kAcc = fast_epi ? EpiCfg<BN, true>::kAcc : EpiCfg<BN, false>::kAcc;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
@@ -717,6 +915,11 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 2); mbar_init(empty_bar + s, 1); }   // A and B producers
         const int arrivals = fast_epi ? EpiCfg<BN, true>::kWarpsPerAcc : EpiCfg<BN, false>::kWarpsPerAcc;
         for (int s = 0; s < kAcc; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, arrivals); }
+        if (ADDK) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_sc) : "memory");
+            if (p.out16) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o16) : "memory");
+            for (int s = 0; s < 2 * kEpiWarps; ++s) mbar_init(sc_bar + s, 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -788,13 +991,16 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // leaving through the staged TMA store (the int8 pipeline); anything else takes the generic body
         const bool fast = fast_epi;
         if (p.rs >= 1) {
-            if (fast && p.add_sc) epilogue<BN, true, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
-            else if (fast && p.bias_c && p.relu) epilogue<BN, true, true, false, 2>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
-            else if (fast && p.bias_c) epilogue<BN, true, true, false, 1>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            if (ADDK) {
+                if (p.bias_c) epilogue_add<BN, true, true>(p, &tmap_o, &tmap_sc, &tmap_o16, smem_o, sc_bar, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+                else epilogue_add<BN, true, false>(p, &tmap_o, &tmap_sc, &tmap_o16, smem_o, sc_bar, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            }
+            else if (fast && p.bias_c && p.relu) epilogue<BN, true, true, 2>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else if (fast && p.bias_c) epilogue<BN, true, true, 1>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else if (fast) epilogue<BN, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else epilogue<BN, true, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
         } else {
-            if (fast && p.add_sc) epilogue<BN, false, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            if (ADDK) epilogue_add<BN, false, false>(p, &tmap_o, &tmap_sc, &tmap_o16, smem_o, sc_bar, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else if (fast) epilogue<BN, false, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else epilogue<BN, false, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
         }
@@ -939,8 +1145,8 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
     } else if (warp < kWarpB) {                        // (warp kWarpB idles: the weights are resident here)
         const bool fast = fast_epi;
         if (p.rs >= 1) {
-            if (fast && p.bias_c && p.relu) epilogue<BN, true, true, false, 2>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
-            else if (fast && p.bias_c) epilogue<BN, true, true, false, 1>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            if (fast && p.bias_c && p.relu) epilogue<BN, true, true, 2>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
+            else if (fast && p.bias_c) epilogue<BN, true, true, 1>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else if (fast) epilogue<BN, true, true>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
             else epilogue<BN, true, false>(p, &tmap_o, smem_o, tmem_full_bar, tmem_empty_bar, tmem_base, total_tiles, n_tiles);
         } else {
@@ -1076,7 +1282,36 @@ int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, 
         if (rc != PQ_OK) return rc;
         p.stage_s8 = 1;
     }
-    kern<<<grid, pq::kGemmThreads, Cfg::kTotal, s>>>(ta, tb, to, p);
+    const CUtensorMap none = {};
+    kern<<<grid, pq::kGemmThreads, Cfg::kTotal, s>>>(ta, tb, to, none, none, p);
+    return (int)cudaGetLastError();
+}
+
+// fused NewConv2d + NewAdd kernels (ADDK): int8 result, shortcut and int16 sum travel as [32 rows][32 channels]
+// boxes per epilogue warp (see epilogue_add); fewer operand stages because the epilogue stages 80 KB
+template <int BN, int BK, int STAGES>
+int launch_cfg_add(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, cudaStream_t s)
+{
+    using Cfg = pq::GemmSmem<BN, BK, STAGES, true>;
+    static_assert(Cfg::kTotal <= 227 * 1024, "shared memory budget");
+    auto kern = pq::gemm_s8_kernel<BN, BK, STAGES, true>;
+    static bool attr = false;
+    if (!attr) {
+        PQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kTotal));
+        attr = true;
+    }
+    const long long tiles = (long long)((p.M + pq::kBM - 1) / pq::kBM) * ((p.N + BN - 1) / BN);
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    CUtensorMap to = {}, tsc = {}, to16 = {};
+    int rc;
+    const uint64_t N = (uint64_t)p.N, M = (uint64_t)p.M;
+    if ((rc = encode_2d(&to, p.out_s8, N, M, N, pq::kAddSlab, 32)) != PQ_OK) return rc;
+    if (p.add_is16) rc = encode_2d(&tsc, p.add_sc, 2 * N, M, 2 * N, 2 * pq::kAddSlab, 32);
+    else rc = encode_2d(&tsc, p.add_sc, N, M, N, pq::kAddSlab, 32);
+    if (rc != PQ_OK) return rc;
+    if (p.out16 && (rc = encode_2d(&to16, p.out16, 2 * N, M, 2 * N, 2 * pq::kAddSlab, 32)) != PQ_OK) return rc;
+    p.stage_s8 = 1;
+    kern<<<grid, pq::kGemmThreads, Cfg::kTotal, s>>>(ta, tb, to, tsc, to16, p);
     return (int)cudaGetLastError();
 }
 
@@ -1084,6 +1319,13 @@ int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, 
 template <int BK>
 int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, int bn, cudaStream_t s)
 {
+    if (p.add_sc) {                                // 80 KB of epilogue staging: <= 144 KB of operand stages
+        switch (bn) {
+            case 256: return launch_cfg_add<256, BK, (BK == 128 ? 3 : (BK == 64 ? 6 : 8))>(ta, tb, p, s);
+            case 128: return launch_cfg_add<128, BK, (BK == 128 ? 4 : 8)>(ta, tb, p, s);
+            default: return launch_cfg_add<64, BK, (BK == 128 ? 6 : 8)>(ta, tb, p, s);
+        }
+    }
     constexpr int S256 = BK == 128 ? 4 : 8;
     constexpr int S128 = BK == 128 ? 6 : 8;
     switch (bn) {
@@ -1221,6 +1463,14 @@ extern "C" int pq_conv2d_s8_add(const int8_t *x_nhwc, const int8_t *w_krsc, cons
 {
     if (!add_host) return PQ_EINVAL;
     return conv_impl(x_nhwc, w_krsc, bias_q, desc_host, 0, nullptr, add_host->out8, add_host, stream);
+}
+
+extern "C" int pq_conv2d_s8_add_ex(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
+                                   const pq_conv_desc *desc_host, const pq_add_desc *add_host, int flags,
+                                   pq_stream_t stream)
+{
+    if (!add_host || (flags & PQ_FLAG_RELU)) return PQ_EINVAL;   // the ReLU of a fused add is add_host->out_relu
+    return conv_impl(x_nhwc, w_krsc, bias_q, desc_host, flags, nullptr, add_host->out8, add_host, stream);
 }
 
 namespace {
