@@ -78,7 +78,8 @@ def main():
             q = _native.quantize_nchw_to_nhwc_s8(x, 4, cpad)
             t_q = 0.0
             sc = torch.randint(-2000, 2000, (B, P, P, cout), dtype=torch.int16, device="cuda")
-            t_c = time_ms(lambda: _native.conv2d_s8_add(q, wk, bias, (s, s), (pad, pad), 9, 4, sc, 5, False, 4, True))
+            # the common case in feat.table: conv output, shortcut and Eltwise all at the same bit
+            t_c = time_ms(lambda: _native.conv2d_s8_add(q, wk, bias, (s, s), (pad, pad), 9, 4, sc, 4, False, 4, True))
         else:
             q = _native.quantize_nchw_to_nhwc_s8(x, 4, cpad)
             t_q = time_ms(lambda: _native.quantize_nchw_to_nhwc_s8(x, 4, cpad))
@@ -86,9 +87,11 @@ def main():
                                                     want_s8=args.s8_out))
         ops = 2.0 * B * P * P * cout * k * k * cin
         out_bytes = B * P * P * cout * (1 if args.s8_out else 4)
+        if args.fused_add and t_q == 0.0:             # all bytes of the fused kernel: A, shortcut int16, int16 + int8 out
+            out_bytes = q.numel() + B * P * P * cout * 5
         qbytes = x.numel() * 4 + q.numel()
         print("%-28s %9.1f %8.3f %8.1f %8.0f %8.3f %8.0f" % ("(%d,%d,%d,%d,%d,%d)x%d" % (cin, h, w, cout, k, s, cnt), ops / 1e9,
-              t_c, ops / t_c / 1e9, out_bytes / t_c / 1e6, t_q, qbytes / t_q / 1e6))
+              t_c, ops / t_c / 1e9, out_bytes / t_c / 1e6, t_q, qbytes / max(t_q, 1e-9) / 1e6))
         tot_conv += t_c * cnt; tot_q += t_q * cnt; tot_ops += ops * cnt
         del x, q, wk
     print("TOTAL conv %.2f ms (%.1f TOPS), quantise %.2f ms, %.2f TOP" % (tot_conv, tot_ops / tot_conv / 1e9, tot_q, tot_ops / 1e12))

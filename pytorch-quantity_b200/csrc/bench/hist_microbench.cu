@@ -200,12 +200,10 @@ int main(int argc, char **argv)
         {
             auto k8 = hist_multi_kernel<1, 8>;
             cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem_bytes(1));
-            for (int agg = 0; agg <= 1; ++agg)
-                for (int cps = 3; cps <= 4; ++cps) {
-                    ms = time_ms([&] { k8<<<148 * cps, kStatThreads, hist_smem_bytes(1)>>>(t, hist, agg); });
-                    printf("  production fast-div VPT=8, %d CTA/SM, aggregate=%d   %8.3f ms  %8.1f GB/s\n", cps, agg, ms,
-                           n * 4.0 / ms / 1e6);
-                }
+            for (int cps = 3; cps <= 4; ++cps) {
+                ms = time_ms([&] { k8<<<148 * cps, kStatThreads, hist_smem_bytes(1)>>>(t, hist); });
+                printf("  production fast-div VPT=8, %d CTA/SM   %8.3f ms  %8.1f GB/s\n", cps, ms, n * 4.0 / ms / 1e6);
+            }
         }
         run_variant<0, 1, 256>("ieee-div, 1 copy, 256thr", x, n, interval, hist, 8);
         run_variant<0, 2, 256>("ieee-div, 2 copies, 256thr", x, n, interval, hist, 8);

@@ -1,6 +1,4 @@
 // pq_stats.cu -- C-ABI entry points for the statistics kernels.
-#include <cstdlib>
-
 #include "pq_stats_kernels.cuh"
 
 namespace {
@@ -106,14 +104,8 @@ extern "C" int pq_hist2048_multi_f32(const float *const *xs_host, const uint64_t
         attr_set = true;
     }
     const int ctas_per_sm = (int)((200 * 1024) / smem) < 8 ? (int)((200 * 1024) / smem) : 8;
-    // warp-aggregated atomics for contended data (see hist_add_agg); PQ_HIST_AGG=0 switches the vote off (A/B runs)
-    static int aggregate = -1;
-    if (aggregate < 0) {
-        const char *e = getenv("PQ_HIST_AGG");
-        aggregate = (e && e[0] == '0') ? 0 : 1;
-    }
     kern<<<grid_for(t.total_chunks, ctas_per_sm), pq::kStatThreads, smem, (cudaStream_t)stream>>>(
-        t, reinterpret_cast<unsigned long long *>(hist), aggregate);
+        t, reinterpret_cast<unsigned long long *>(hist));
     return (int)cudaGetLastError();
 }
 

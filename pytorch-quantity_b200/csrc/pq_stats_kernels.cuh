@@ -299,43 +299,6 @@ __device__ __forceinline__ bool hist_add_fast(unsigned int base_addr, unsigned i
     return ZERO_AWARE ? (slow && v != 0.0f) : slow;
 }
 
-// Contended data (a heavy-tailed tensor whose mass sits in a handful of bins, or one dominated by exact zeros): the 32
-// lanes of a warp hit only a few distinct counters and their shared atomics serialise.  This variant lets the lanes
-// that target the same counter elect one of them (MATCH.ANY), which adds the group's population count in a single
-// atomic.  It costs four more instructions per element, so a warp uses it only while a vote on the first element of
-// its current chunk part says that at least eight lanes share a counter.
-template <bool ZERO_AWARE>
-__device__ __forceinline__ bool hist_add_agg(unsigned int base_addr, unsigned int trash_addr, float v, const HistDiv &h,
-                                             unsigned int lanemask_lt)
-{
-    const unsigned int bits = hist_fast_bits(v, h);
-    const bool slow = hist_is_slow(bits);
-    unsigned int addr = hist_fast_addr(bits, base_addr);
-    if (ZERO_AWARE) addr = slow ? trash_addr : addr;
-    const unsigned int peers = __match_any_sync(0xffffffffu, addr);
-    if ((peers & lanemask_lt) == 0u)
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(__popc(peers)) : "memory");
-    return ZERO_AWARE ? (slow && v != 0.0f) : slow;
-}
-
-template <bool ZERO_AWARE, int VPT>
-__device__ __forceinline__ unsigned int hist_add_vecs_agg(unsigned int base_addr, unsigned int trash_addr,
-                                                          const float4 (&v)[VPT], const HistDiv &h)
-{
-    unsigned int lanemask_lt;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanemask_lt));
-    unsigned int redo = 0;
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-        const bool s0 = hist_add_agg<ZERO_AWARE>(base_addr, trash_addr, v[i].x, h, lanemask_lt);
-        const bool s1 = hist_add_agg<ZERO_AWARE>(base_addr, trash_addr, v[i].y, h, lanemask_lt);
-        const bool s2 = hist_add_agg<ZERO_AWARE>(base_addr, trash_addr, v[i].z, h, lanemask_lt);
-        const bool s3 = hist_add_agg<ZERO_AWARE>(base_addr, trash_addr, v[i].w, h, lanemask_lt);
-        if (s0 | s1 | s2 | s3) redo |= 1u << i;
-    }
-    return redo;
-}
-
 // redo pass for one element of a flagged float4 (rare)
 template <bool ZERO_AWARE>
 __device__ __forceinline__ void hist_redo(unsigned int *sh, unsigned int base_addr, float v, const HistDiv &h)
@@ -397,7 +360,7 @@ constexpr size_t hist_smem_bytes(int copies) { return 8192 + (size_t)copies * PQ
 
 template <int COPIES, int VPT = kVecPerThread>
 __global__ void __launch_bounds__(kStatThreads, VPT <= 4 ? 6 : 4)
-hist_multi_kernel(const __grid_constant__ SegTable tab, unsigned long long *__restrict__ hist, const int aggregate)
+hist_multi_kernel(const __grid_constant__ SegTable tab, unsigned long long *__restrict__ hist)
 {
     // dynamic shared memory: hist_smem_bytes(COPIES)
     extern __shared__ unsigned int s_raw[];                // 8 KB alignment slack + [COPIES][2048] + trash
@@ -435,25 +398,7 @@ hist_multi_kernel(const __grid_constant__ SegTable tab, unsigned long long *__re
                     float4 v[VPT];
 #pragma unroll
                     for (int i = 0; i < VPT; ++i) v[i] = ld_stream_f4(psrc + threadIdx.x + i * kStatThreads);
-                    // vote: how many lanes share the counter of this part's first element?
-                    bool contended = false;
-                    if (aggregate) {
-                        unsigned int a0 = hist_fast_addr(hist_fast_bits(v[0].x, hd), mine_addr);
-                        if (zero_aware && v[0].x == 0.0f) a0 = trash_addr;
-                        contended = __any_sync(0xffffffffu, __popc(__match_any_sync(0xffffffffu, a0)) >= 8);
-                    }
-                    if (contended) {
-                        if (zero_aware) {
-                            const unsigned int redo = hist_add_vecs_agg<true, VPT>(mine_addr, trash_addr, v, hd);
-                            hist_redo_vecs<true>(redo, mine, mine_addr, psrc, hd);
-                        } else {
-                            const unsigned int redo = hist_add_vecs_agg<false, VPT>(mine_addr, trash_addr, v, hd);
-                            bool many_zeros = false;
-                            if (__popc(redo) >= 3) many_zeros = hist_flagged_has_zero(redo, psrc);
-                            zero_aware = __any_sync(0xffffffffu, many_zeros);
-                            hist_redo_vecs<false>(redo, mine, mine_addr, psrc, hd);
-                        }
-                    } else if (zero_aware) {
+                    if (zero_aware) {
                         const unsigned int redo = hist_add_vecs<true, VPT>(mine_addr, trash_addr, v, hd);
                         hist_redo_vecs<true>(redo, mine, mine_addr, psrc, hd);
                     } else {

@@ -232,3 +232,68 @@ def test_c1_resnet18_calibration_vs_reference_run(tmp_path):
     for name, val in ref.items():
         if name.startswith("weight/"):                       # int8 weights: independent of the activation tables
             assert hashlib.md5(snap[name]).hexdigest() == val["md5"], name
+
+
+class _InplaceNet(torch.nn.Module):
+    """conv -> ReLU(inplace) -> conv -> ReLU(inplace) -> avgpool -> view -> fc: the in-place ReLUs overwrite the
+    hooked conv outputs after their hooks fired (the reference snapshots to numpy at hook time and is immune)."""
+
+    def __init__(self, inplace):
+        super().__init__()
+        import common.quantity as cq
+        nn = torch.nn
+        torch.manual_seed(3)
+        self.c1 = nn.Conv2d(3, 8, 3, padding=1)
+        self.r1 = nn.ReLU(inplace)
+        self.c2 = nn.Conv2d(8, 8, 3, padding=1)
+        self.r2 = nn.ReLU(inplace)
+        self.pool = nn.AvgPool2d(8)
+        self.view = cq.View()
+        self.fc = nn.Linear(8, 4)
+
+    def forward(self, x):
+        return self.fc(self.view(self.pool(self.r2(self.c2(self.r1(self.c1(x)))))))
+
+
+def test_inplace_relu_records_pre_modification_values(tmp_path):
+    """calibration hooks keep device references; tensors a later in-place op overwrites are found by the
+    tracing forward and cloned at hook time, so the statistics are those of the out-of-place model (what the reference
+    records, pytorch_quantizer.py:509,513)."""
+    import tools
+    batches = [(torch.randn(4, 3, 8, 8, generator=torch.Generator().manual_seed(10 + i)), None) for i in range(2)]
+    results = {}
+    for inplace in (False, True):
+        cfg, user = _configs(tmp_path / ("ip%d" % inplace), (1, 3, 8, 8), 1)
+        with torch.no_grad():
+            q = tools.Quantity(_InplaceNet(inplace).eval(), config=cfg, user_config=user, verbose=False)
+            assert bool(q._inplace_modified) == inplace
+            q.activation_quantize(batches)
+        results[inplace] = q.last_calibration
+    a, b = results[False], results[True]
+    assert a["table_lines"] == b["table_lines"] and a["top_feat_names"] == b["top_feat_names"]
+    for n in a["top_feat_names"]:
+        assert float(a["max_vals"][n]) == float(b["max_vals"][n]), n
+        assert np.array_equal(a["distributions"][n], b["distributions"][n]), n
+    # the conv outputs are signed: had the post-ReLU values been recorded, half of the mass would be missing
+    assert a["distributions"]["Conv2d_1"].sum() == 2 * 4 * 8 * 8 * 8
+
+
+def test_calibration_hooks_reset_themselves_between_plain_forwards(tmp_path):
+    """regist_hook_outfeature used the way the reference allows (:491-524): the caller runs model(x)
+    directly, several times; names must not keep growing and 'image' must be the latest input."""
+    import tools
+    cfg, user = _configs(tmp_path, (1, 3, 8, 8), 1)
+    with torch.no_grad():
+        net = _InplaceNet(False).eval()
+        q = tools.Quantity(net, config=cfg, user_config=user, verbose=False)
+        feats, hooks = q.regist_hook_outfeature(q.model)
+        keys = None
+        for i in range(3):
+            x = torch.randn(2, 3, 8, 8, generator=torch.Generator().manual_seed(50 + i)).cuda()
+            q.model(x)
+            if keys is None:
+                keys = list(feats)
+            assert list(feats) == keys and torch.equal(feats["image"], x)
+        for h in hooks:
+            h.remove()
+    assert keys == ["image", "Conv2d_1", "Conv2d_3", "Linear_7"]
