@@ -101,6 +101,13 @@ __device__ __forceinline__ void tma_load_2d_a(const CUtensorMap *map, uint32_t b
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_a(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_5d_a(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
                                               int c3, int c4)
 {
@@ -269,6 +276,12 @@ struct GemmParams {
     int num_kb;                // K blocks of BK bytes
     int a_im2col;              // 0: A is a 2-D [M][K] tile source; 1: im2col over NHWC; 2: row windows (below)
     int R, S, cblocks;         // filter taps and BK-blocks per tap (im2col mode)
+    int b_resident;            // the whole B operand of the CTA (one n tile, num_kb <= ring slots) is loaded ONCE into the
+                               // ring's B slots and stays there: short-K 3x3 layers are bound by L2 -> SM traffic (the
+                               // im2col gather re-reads every input byte R*S times), of which the per-tile weight
+                               // re-fetch was a third
+    int tps;                   // K blocks per pipeline stage (im2col mode): one mbarrier round trip moves tps A tiles and tps
+                               // B tiles (3 for short-K 3x3 layers, whose K block holds only ~70 cycles of tensor work)
     int C;                     // padded channels (bytes per pixel)
     int P, Q;                  // output height / width (im2col mode)
     int stride_h, stride_w, pad_h, pad_w;
@@ -351,14 +364,17 @@ constexpr int kAddO8Bytes = 32 * kAddSlab;                     // 1 KB
 constexpr int kAddS16Bytes = 32 * kAddSlab * 2;                // 2 KB
 constexpr int kAddWarpBytes = kAddO8Bytes + 2 * kAddS16Bytes;  // 5 KB
 
-template <int BN, int BK, int STAGES, bool ADDK = false>
+// BSLOTS: B-operand ring slots.  Normally one per A slot; the "deep A" configuration of short-K 3x3 layers keeps the
+// whole B operand resident in 9 slots and spends the rest of shared memory on A slots (bytes in flight: these layers
+// are bound by the latency of the im2col gather, 72 KB in flight per SM moved only one tile per TMA round trip).
+template <int BN, int BK, int STAGES, bool ADDK = false, int BSLOTS = STAGES>
 struct GemmSmem {
     static constexpr int kABytes = kBM * BK;
     static constexpr int kBBytes = BN * BK;
-    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kRingBytes = STAGES * kABytes + BSLOTS * kBBytes;
     static constexpr int kOutBytes = ADDK ? kEpiWarps * kAddWarpBytes
                                           : kEpiWarps * EpiCfg<BN, true>::kSlabBytes;   // warp-private int8 staging slabs (FAST is the larger)
-    static constexpr size_t kTotal = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + kOutBytes + 512 /*barriers*/;
+    static constexpr size_t kTotal = 1024 /*align slack*/ + (size_t)kRingBytes + kOutBytes + 768 /*barriers*/;
 };
 
 
@@ -602,6 +618,39 @@ __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+
+// One 16-column chunk of the fused add once the convolution result (pk) and the shortcut (sc) are in registers as
+// packed s16x2 pairs.  OUT_RELU / FASTQ are compile-time so that the common case (ReLU after the Eltwise, Eltwise bit ==
+// sum bit) is a straight line of 1.25 packed instructions per element; everything else takes the general 32-bit
+// requantisation.
+template <bool OUT_RELU, bool FASTQ>
+__device__ __forceinline__ void add_chunk(const uint32_t (&pk)[8], const uint32_t (&sc)[8], uint32_t s_hi2, uint32_t s_lo2,
+                                          int qshift, int d, int rc, uint32_t (&sum)[8], uint32_t (&o)[4])
+{
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        sum[q] = OUT_RELU ? __viaddmin_s16x2_relu(pk[q], sc[q], s_hi2)
+                          : __vmaxs2(__viaddmin_s16x2(pk[q], sc[q], s_hi2), s_lo2);
+    if (FASTQ) {                                       // same bit: saturate the pairs, keep the low bytes
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t w0 = __vmins2(sum[2 * q], 0x007f007fu), w1 = __vmins2(sum[2 * q + 1], 0x007f007fu);
+            if (!OUT_RELU) { w0 = __vmaxs2(w0, 0xff80ff80u); w1 = __vmaxs2(w1, 0xff80ff80u); }
+            o[q] = __byte_perm(w0, w1, 0x6420);
+        }
+    } else {                                           // general requantisation in 32 bits (ties to even / left shift)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int e[4] = {(int)(short)(sum[2 * q] & 0xffffu), (int)sum[2 * q] >> 16,
+                        (int)(short)(sum[2 * q + 1] & 0xffffu), (int)sum[2 * q + 1] >> 16};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                e[u] = d ? (e[u] + rc + ((e[u] >> d) & 1)) >> d : max(-128, min(127, e[u])) << qshift;
+            o[q] = pack4_sat_s8(e[0], e[1], e[2], e[3]);
+        }
+    }
+}
+
 template <int BN, bool POS, bool FOLD>
 __device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensorMap *tmap_o, const CUtensorMap *tmap_sc,
                                              const CUtensorMap *tmap_o16, uint8_t *smem_o, uint64_t *sc_bar_all,
@@ -622,7 +671,7 @@ __device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensor
     const bool sc16 = p.add_is16 != 0;
     const uint32_t sc_bytes = sc16 ? (uint32_t)kAddS16Bytes : (uint32_t)kAddO8Bytes;
     // constants of the packed arithmetic
-    const int cmul = 1 << p.add_cshift;
+    const int cmul = 1 << p.add_cshift;                // (bounds of the scaled conv result; the scaling itself is a shift)
     const uint32_t y_hi2 = (uint32_t)(127 * cmul) * 0x10001u, y_lo2 = ((uint32_t)(-128 * cmul) & 0xffffu) * 0x10001u;
     const uint32_t s_hi2 = (uint32_t)p.add_hi * 0x10001u, s_lo2 = ((uint32_t)p.add_lo & 0xffffu) * 0x10001u;
     const bool out_relu = p.add_lo == 0;
@@ -714,11 +763,17 @@ __device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensor
                             y[4 * q + 3] = requant_t<POS>((int)a[4 * q + 3], rq, b4.w);
                         }
                     }
-                    // (r + b) is within [-256, 254]: scale, pack, then the second saturation on the packed pairs
+                    // (r + b) is within [-256, 254]: scale (only when the sum lives at a finer bit), pack, then the
+                    // second saturation on the packed pairs
+                    if (p.add_cshift == 0) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t w = pack2_sat_s16(y[2 * q + 1] * cmul, y[2 * q] * cmul);
-                        pk[j][q] = __vmaxs2(__vmins2(w, y_hi2), y_lo2);
+                        for (int q = 0; q < 8; ++q)
+                            pk[j][q] = __vmaxs2(__vmins2(pack2_sat_s16(y[2 * q + 1], y[2 * q]), y_hi2), y_lo2);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            pk[j][q] = __vmaxs2(__vmins2(pack2_sat_s16(y[2 * q + 1] << p.add_cshift, y[2 * q] << p.add_cshift),
+                                                         y_hi2), y_lo2);
                     }
                 } else {
 #pragma unroll
@@ -762,43 +817,35 @@ __device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensor
                 }
                 if (nt >= 0 && lane == 0) issue_load(cur ^ 1, nt, ns);
             }
+            if (p.add_sc_relu) {                       // a pending nn.ReLU on the shortcut operand
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) sc[j][q] = __vmaxs2(sc[j][q], 0u);
+            }
+            if (p.add_sshift) {                        // rare: shortcut at a coarser bit than the sum
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int lo16 = (int)(short)(sc[j][q] & 0xffffu), hi16 = (int)sc[j][q] >> 16;
+                        sc[j][q] = pack2_sat_s16(hi16 << p.add_sshift, lo16 << p.add_sshift);
+                    }
+            }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (colb + 16 * j >= p.N) continue;
-                uint32_t sum[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    uint32_t sv = sc[j][q];
-                    if (p.add_sc_relu) sv = __vmaxs2(sv, 0u);
-                    if (p.add_sshift) {                // rare: shortcut at a coarser bit than the sum
-                        const int lo16 = (int)(short)(sv & 0xffffu), hi16 = (int)sv >> 16;
-                        sv = pack2_sat_s16(hi16 << p.add_sshift, lo16 << p.add_sshift);
-                    }
-                    sum[q] = out_relu ? __viaddmin_s16x2_relu(pk[j][q], sv, s_hi2)
-                                      : __vmaxs2(__viaddmin_s16x2(pk[j][q], sv, s_hi2), s_lo2);
+                uint32_t sum[8], o[4];
+                if (p.add_qshift == 0) {
+                    if (out_relu) add_chunk<true, true>(pk[j], sc[j], s_hi2, s_lo2, 0, 0, 0, sum, o);
+                    else add_chunk<false, true>(pk[j], sc[j], s_hi2, s_lo2, 0, 0, 0, sum, o);
+                } else {
+                    if (out_relu) add_chunk<true, false>(pk[j], sc[j], s_hi2, s_lo2, p.add_qshift, d, rc, sum, o);
+                    else add_chunk<false, false>(pk[j], sc[j], s_hi2, s_lo2, p.add_qshift, d, rc, sum, o);
                 }
                 if (p.out16) {
                     sts_u4(sbuf + off16(2 * j), sum[0], sum[1], sum[2], sum[3]);
                     sts_u4(sbuf + off16(2 * j + 1), sum[4], sum[5], sum[6], sum[7]);
-                }
-                uint32_t o[4];
-                if (p.add_qshift == 0) {               // same bit: saturate the pairs, keep the low bytes
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t w0 = __vmins2(sum[2 * q], 0x007f007fu), w1 = __vmins2(sum[2 * q + 1], 0x007f007fu);
-                        if (!out_relu) { w0 = __vmaxs2(w0, 0xff80ff80u); w1 = __vmaxs2(w1, 0xff80ff80u); }
-                        o[q] = __byte_perm(w0, w1, 0x6420);
-                    }
-                } else {                               // general requantisation in 32 bits (ties to even / left shift)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        int e[4] = {(int)(short)(sum[2 * q] & 0xffffu), (int)sum[2 * q] >> 16,
-                                    (int)(short)(sum[2 * q + 1] & 0xffffu), (int)sum[2 * q + 1] >> 16};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            e[u] = d ? (e[u] + rc + ((e[u] >> d) & 1)) >> d : max(-128, min(127, e[u])) << p.add_qshift;
-                        o[q] = pack4_sat_s8(e[0], e[1], e[2], e[3]);
-                    }
                 }
                 sts_u4(o8_base + off8(j), o[0], o[1], o[2], o[3]);
             }
@@ -862,44 +909,48 @@ __device__ __forceinline__ void produce_a(const GemmParams &p, const CUtensorMap
         }
         const int w0 = wq * p.stride_w - p.pad_w, h0 = hp * p.stride_h - p.pad_h;
         int r = 0, s = 0, cb = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int tps = MODE == 1 ? p.tps : 1, nss = STAGES / tps;       // stages of tps consecutive ring slots
+        for (int kb = 0; kb < p.num_kb; kb += tps) {
             mbar_wait(empty_bar + stage, phase ^ 1);
-            if (leader) {
-                const uint32_t bar = full_base + (uint32_t)stage * 8u;
-                const uint32_t dst = a_base + (uint32_t)stage * kABytes;
-                mbar_expect_tx_a(bar, kABytes);
-                if (MODE == 2)                 // filter row kb: padded input row = p * stride_h + kb
-                    tma_load_5d_a(tmap_a, bar, dst, 0, wq, hp + kb / p.stride_h, kb % p.stride_h, nb);
-                else if (MODE == 1)
-                    tma_load_im2col_4d_a(tmap_a, bar, dst, cb * BK, w0, h0, nb, (uint16_t)(s * p.dil_w),
-                                         (uint16_t)(r * p.dil_h));
-                else
-                    tma_load_2d_a(tmap_a, bar, dst, kb * BK, m0);
+            const uint32_t bar = full_base + (uint32_t)stage * 8u;
+            if (leader) mbar_expect_tx_a(bar, kABytes * (uint32_t)tps);
+            for (int t = 0; t < tps; ++t) {
+                if (leader) {
+                    const uint32_t dst = a_base + (uint32_t)(stage * tps + t) * kABytes;
+                    if (MODE == 2)             // filter row kb: padded input row = p * stride_h + kb
+                        tma_load_5d_a(tmap_a, bar, dst, 0, wq, hp + kb / p.stride_h, kb % p.stride_h, nb);
+                    else if (MODE == 1)
+                        tma_load_im2col_4d_a(tmap_a, bar, dst, cb * BK, w0, h0, nb, (uint16_t)(s * p.dil_w),
+                                             (uint16_t)(r * p.dil_h));
+                    else
+                        tma_load_2d_a(tmap_a, bar, dst, kb * BK, m0);
+                }
+                if (MODE == 1) { if (++cb == p.cblocks) { cb = 0; if (++s == p.S) { s = 0; ++r; } } }
             }
-            if (MODE == 1) { if (++cb == p.cblocks) { cb = 0; if (++s == p.S) { s = 0; ++r; } } }
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == nss) { stage = 0; phase ^= 1; }
         }
     }
 }
 
-template <int BN, int BK, int STAGES, bool ADDK = false>
+template <int BN, int BK, int STAGES, bool ADDK = false, int BSLOTS = STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)     // 19 warps = 5 on one SM sub-partition: <= 104 registers / thread
 gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_sc,
                const __grid_constant__ CUtensorMap tmap_o16, const GemmParams p)
 {
-    using Cfg = GemmSmem<BN, BK, STAGES, ADDK>;
+    using Cfg = GemmSmem<BN, BK, STAGES, ADDK, BSLOTS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + (size_t)STAGES * Cfg::kABytes;
-    uint8_t *smem_o = smem + (size_t)STAGES * Cfg::kStageBytes;          // 1024-byte aligned
+    uint8_t *smem_o = smem + (size_t)Cfg::kRingBytes;                    // 1024-byte aligned
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_o + Cfg::kOutBytes);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *tmem_full_bar = empty_bar + STAGES;      // [kAcc]
     uint64_t *tmem_empty_bar = tmem_full_bar + 4;      // [kAcc]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 4);
     uint64_t *sc_bar = tmem_empty_bar + 5;             // [kEpiWarps][2] shortcut-slab barriers (ADDK kernels only)
+    uint64_t *bres_bar = sc_bar + 2 * kEpiWarps;       // resident-B arrival
     const bool fast_epi = ADDK || (p.stage_s8 && !p.out_f32);          // which epilogue configuration runs
     const int kAcc = fast_epi ? EpiCfg<BN, true>::kAcc : EpiCfg<BN, false>::kAcc;
 
@@ -912,7 +963,8 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         if (p.stage_s8) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 2); mbar_init(empty_bar + s, 1); }   // A and B producers
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, p.b_resident ? 1 : 2); mbar_init(empty_bar + s, 1); }   // A and B producers
+        mbar_init(bres_bar, 1);
         const int arrivals = fast_epi ? EpiCfg<BN, true>::kWarpsPerAcc : EpiCfg<BN, false>::kWarpsPerAcc;
         for (int s = 0; s < kAcc; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, arrivals); }
         if (ADDK) {
@@ -942,16 +994,34 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool leader = elect_one();
         int stage = 0; uint32_t phase = 0;
         const uint32_t b_base = smem_u32(smem_b), full_base = smem_u32(full_bar);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (p.b_resident) {                            // all K blocks of the (single) n tile, once; slot == K block
+            if (leader) {
+                const uint32_t bar = smem_u32(bres_bar);
+                const int tps = p.a_im2col == 1 ? p.tps : 1;
+                mbar_expect_tx_a(bar, (uint32_t)Cfg::kBBytes * (uint32_t)p.num_kb);
+                for (int kb = 0; kb < p.num_kb; kb += tps) {
+                    const uint32_t dst = b_base + (uint32_t)kb * (uint32_t)Cfg::kBBytes;
+                    if (tps == 1) tma_load_2d_a(&tmap_b, bar, dst, kb * BK, 0);
+                    else tma_load_3d_a(&tmap_b, bar, dst, 0, 0, kb);
+                }
+            }
+            __syncwarp();
+        }
+        for (int tile = blockIdx.x; tile < total_tiles && !p.b_resident; tile += gridDim.x) {
             const int n0 = (n_tiles == 1 ? 0 : tile % n_tiles) * BN;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
+            const int tps = p.a_im2col == 1 ? p.tps : 1, nss = STAGES / tps;
+            for (int kb = 0; kb < p.num_kb; kb += tps) {
                 mbar_wait(empty_bar + stage, phase ^ 1);
                 if (leader) {
                     const uint32_t bar = full_base + (uint32_t)stage * 8u;
-                    mbar_expect_tx_a(bar, Cfg::kBBytes);
-                    tma_load_2d_a(&tmap_b, bar, b_base + (uint32_t)stage * (uint32_t)Cfg::kBBytes, kb * BK, n0);
+                    const uint32_t dst = b_base + (uint32_t)(stage * tps) * (uint32_t)Cfg::kBBytes;
+                    mbar_expect_tx_a(bar, (uint32_t)Cfg::kBBytes * (uint32_t)tps);
+                    // tps > 1: the map is [K block][N][BK] and one box brings tps consecutive K blocks, each as its
+                    // own [BN][BK] tile in consecutive ring slots
+                    if (tps == 1) tma_load_2d_a(&tmap_b, bar, dst, kb * BK, n0);
+                    else tma_load_3d_a(&tmap_b, bar, dst, 0, n0, kb);
                 }
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == nss) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -962,24 +1032,28 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t empty_base = smem_u32(empty_bar), tfull_base = smem_u32(tmem_full_bar);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
+        if (p.b_resident) mbar_wait(bres_bar, 0);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);      // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-            for (int kb = 0; kb < p.num_kb; ++kb) {
+            const int tps = p.a_im2col == 1 ? p.tps : 1, nss = STAGES / tps;
+            for (int kb = 0; kb < p.num_kb; kb += tps) {
                 mbar_wait(full_bar + stage, phase);
                 tc_fence_after();
                 if (leader) {
-                    // the 14-bit start-address field advances by bytes / 16 (shared addresses stay below 2^18)
-                    const uint64_t da = da0 + (uint64_t)(uint32_t)(stage * (Cfg::kABytes >> 4));
-                    const uint64_t db = db0 + (uint64_t)(uint32_t)(stage * (Cfg::kBBytes >> 4));
+                    for (int t = 0; t < tps; ++t) {
+                        // the 14-bit start-address field advances by bytes / 16 (shared addresses stay below 2^18)
+                        const uint64_t da = da0 + (uint64_t)(uint32_t)((stage * tps + t) * (Cfg::kABytes >> 4));
+                        const uint64_t db = db0 + (uint64_t)(uint32_t)((p.b_resident ? kb + t : stage * tps + t) * (Cfg::kBBytes >> 4));
 #pragma unroll
-                    for (int k = 0; k < BK / 32; ++k)  // UMMA_K = 32 int8: advance 32 B inside the swizzle span
-                        umma_i8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    umma_commit_a(empty_base + (uint32_t)stage * 8u);    // frees the smem slot when these MMAs retire
+                        for (int k = 0; k < BK / 32; ++k)  // UMMA_K = 32 int8: advance 32 B inside the swizzle span
+                            umma_i8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | t | k) != 0);
+                    }
+                    umma_commit_a(empty_base + (uint32_t)stage * 8u);    // frees the smem slots when these MMAs retire
                 }
                 __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == nss) { stage = 0; phase ^= 1; }
             }
             if (leader) umma_commit_a(tfull_base + (uint32_t)acc * 8u);  // accumulator complete
             __syncwarp();
@@ -1250,12 +1324,12 @@ int num_sms()
     return n;
 }
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, int BSLOTS = STAGES>
 int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, cudaStream_t s)
 {
-    using Cfg = pq::GemmSmem<BN, BK, STAGES>;
+    using Cfg = pq::GemmSmem<BN, BK, STAGES, false, BSLOTS>;
     static_assert(Cfg::kTotal <= 227 * 1024, "shared memory budget");
-    auto kern = pq::gemm_s8_kernel<BN, BK, STAGES>;
+    auto kern = pq::gemm_s8_kernel<BN, BK, STAGES, false, BSLOTS>;
     static bool attr = false;
     if (!attr) {
         PQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kTotal));
@@ -1263,6 +1337,8 @@ int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, 
     }
     const long long tiles = (long long)((p.M + pq::kBM - 1) / pq::kBM) * ((p.N + BN - 1) / BN);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());     // persistent: one CTA per SM
+    p.b_resident = (p.a_im2col != 2 && p.N <= BN && p.num_kb <= BSLOTS) ? 1 : 0;
+    if (BSLOTS != STAGES && !p.b_resident) return PQ_EUNSUPPORTED;      // deep-A configurations need the resident B
     // int8 output tile: [128 rows][min(BN, 128) bytes] boxes of the row-major [M][N] result
     CUtensorMap to = {};
     p.stage_s8 = 0;
@@ -1302,6 +1378,7 @@ int launch_cfg_add(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams 
     }
     const long long tiles = (long long)((p.M + pq::kBM - 1) / pq::kBM) * ((p.N + BN - 1) / BN);
     const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    p.b_resident = (p.N <= BN && p.num_kb <= STAGES) ? 1 : 0;
     CUtensorMap to = {}, tsc = {}, to16 = {};
     int rc;
     const uint64_t N = (uint64_t)p.N, M = (uint64_t)p.M;
@@ -1326,13 +1403,18 @@ int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, i
             default: return launch_cfg_add<64, BK, (BK == 128 ? 6 : 8)>(ta, tb, p, s);
         }
     }
-    constexpr int S256 = BK == 128 ? 4 : 8;
-    constexpr int S128 = BK == 128 ? 6 : 8;
+    // ring slots; for BK <= 64 a multiple of three where it fits (stages of three K blocks, GemmParams::tps)
+    constexpr int S256 = BK == 128 ? 4 : (BK == 64 ? 8 : 9);
+    constexpr int S128 = BK == 128 ? 6 : 9;
+    constexpr int S64 = BK == 128 ? 8 : 9;
+    // short-K 3x3 layers (C = 64, N <= 64: ResNet's first stage): resident weights, 18 A slots = 144 KB in flight
+    if (BK == 64 && bn == 64 && p.a_im2col == 1 && p.N <= 64 && p.num_kb <= 9 && p.tps == 3)
+        return launch_cfg<64, 64, 18, 9>(ta, tb, p, s);
     switch (bn) {
         case 256: return launch_cfg<256, BK, S256>(ta, tb, p, s);
         case 128: return launch_cfg<128, BK, S128>(ta, tb, p, s);
-        case 64: return launch_cfg<64, BK, 8>(ta, tb, p, s);
-        default: return launch_cfg<32, BK, 8>(ta, tb, p, s);
+        case 64: return launch_cfg<64, BK, S64>(ta, tb, p, s);
+        default: return launch_cfg<32, BK, S64>(ta, tb, p, s);
     }
 }
 
@@ -1504,10 +1586,20 @@ int conv_impl(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
     CUtensorMap ta, tb;
     if ((rc = encode_im2col(&ta, x_nhwc, d, bk, dil_h, dil_w)) != PQ_OK) return rc;
     const uint64_t ktot = (uint64_t)d.R * d.S * d.C;
-    if ((rc = encode_2d(&tb, w_krsc, ktot, d.K, ktot, bk, bn)) != PQ_OK) return rc;
     pq::GemmParams p = {};
     p.M = (int)M; p.N = d.K; p.a_im2col = 1;
     p.R = d.R; p.S = d.S; p.C = d.C; p.cblocks = d.C / bk; p.num_kb = d.R * d.S * p.cblocks;
+    // short K blocks (<= 64 bytes of K: ~70 cycles of tensor work per block at BN = 64) are bound by the producers'
+    // per-stage mbarrier round trip, not by TMA or the tensor pipe: move three K blocks per stage
+    p.tps = (bk <= 64 && p.num_kb % 3 == 0) ? 3 : 1;
+    if (p.tps == 1) {
+        if ((rc = encode_2d(&tb, w_krsc, ktot, d.K, ktot, bk, bn)) != PQ_OK) return rc;
+    } else {                                     // weights as [K block][N][bk]: box = tps blocks x bn filters x bk bytes
+        const cuuint64_t bdims[3] = {(cuuint64_t)bk, (cuuint64_t)d.K, (cuuint64_t)p.num_kb};
+        const cuuint64_t bstr[2] = {(cuuint64_t)ktot, (cuuint64_t)bk};
+        const cuuint32_t bbox[3] = {(cuuint32_t)bk, (cuuint32_t)bn, (cuuint32_t)p.tps};
+        if ((rc = encode_nd(&tb, w_krsc, 3, bdims, bstr, bbox, bk)) != PQ_OK) return rc;
+    }
     p.P = d.P; p.Q = d.Q; p.stride_h = d.stride_h; p.stride_w = d.stride_w; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
     p.dil_h = dil_h; p.dil_w = dil_w;
     p.rs = d.rs; p.ob = d.ob; p.hw = d.P * d.Q; p.bias = bias_q; p.out_f32 = out_f32_nchw; p.out_s8 = out_s8_nhwc;
