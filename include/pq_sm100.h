@@ -178,13 +178,17 @@ int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias
  * its producer's output_bit in feat.table, tools/pytorch_quantizer.py:468-485).
  * PQ_FLAG_RELU fuses a following nn.ReLU into the GEMM / conv epilogue: y = max(y, 0). */
 #define PQ_FLAG_RELU 1
-/* PQ_FLAG_BIAS_FOLDED: bias_q points to int32 [2][N] written by pq_bias_fold_s32 for the SAME rs (N % 4 == 0):
+/* PQ_FLAG_BIAS_FOLDED: bias_q points to int32 [3][N] written by pq_bias_fold_s32 for the SAME rs (N % 16 == 0):
  *   [0] bias   [1] 2^(rs-1) + (bias << rs)
+ *   [2] N/2 words of s16x2 pairs (channels 2j, 2j+1)  h = 127 + min(bias, 0),  then N/2 words of pairs
+ *       l = -128 + max(bias, 0)
  * The int8-only (staged) epilogue then folds BiasAdd (new_quantity_op.py:128-131) into the rounding add of
- * RightShift (:30-37) and applies RightShift's saturation (:41) to the accumulator, where its bounds do not
- * depend on the channel -- the same integers with one ALU operation less per element.
- * Ignored unless 1 <= rs <= 20 and N % 4 == 0. */
+ * RightShift (:30-37),  t = (acc + [1] + (acc >> 31)) >> rs = round_half_away(acc / 2^rs) + bias,  and replaces both
+ * saturations (:41, :71-91) by  clamp(t, l, h)  on packed 16-bit pairs -- the same integers (the composition
+ * Sp(Sp(r) + b) is monotone in r and constant beyond the int8 range of r) with two ALU operations less per element.
+ * Ignored unless 1 <= rs <= 20 and N % 16 == 0. */
 #define PQ_FLAG_BIAS_FOLDED 2
+/* out: int32 [3 * n] (rows [0], [1], [2] above; n even). */
 int pq_bias_fold_s32(const int32_t *bias_q, int n, int rs, int32_t *out, pq_stream_t stream);
 int pq_gemm_s8_ex(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs,
                   int ob, int hw, int flags, float *out_f32, int8_t *out_s8, pq_stream_t stream);

@@ -86,9 +86,9 @@ def absmax_c(x, cur=0.0):
 
 
 def absmax_per_channel(x, channel_dim=1, cur=None):
-    """Extension of a1 with NO reference counterpart (the reference reduces per tensor only,
-    cq/distribution_collector.py:77): the same ``max(|max x|, |min x|)`` taken per channel.
-    Parity for it is therefore unpinned by the reference; this numpy statement is its contract."""
+    """Extension of a1: the reference reduces per tensor only (cq/distribution_collector.py:77); this is the same
+    ``max(|max x|, |min x|)`` taken per channel.  Pinned BY COMPOSITION: tests/golden/channel_max.npz holds the
+    unmodified reference collector run on every channel slice as a tensor of its own (gen_golden.py::gen_channel)."""
     x = np.asarray(x, dtype=np.float32)
     axes = tuple(a for a in range(x.ndim) if a != channel_dim % x.ndim)
     m = np.maximum(np.abs(x.max(axis=axes)), np.abs(x.min(axis=axes))).astype(np.float32)

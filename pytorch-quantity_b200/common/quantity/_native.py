@@ -236,21 +236,21 @@ def kl_search(counts_f64, want_curves=False):
 
 
 def bias_fold(bias_i32, rs):
-    """int32 [N] quantised bias -> int32 [2N]: the bias followed by 2^(rs-1) + (bias << rs), the per-channel
-    constant of the folded int8 epilogue (PQ_FLAG_BIAS_FOLDED, include/pq_sm100.h).  Returned unchanged when the
-    fold does not apply (N % 4 != 0 or rs outside [1, 20])."""
+    """int32 [N] quantised bias -> int32 [3N]: the bias, then 2^(rs-1) + (bias << rs) (the per-channel constant
+    of the folded int8 epilogue), then the post-shift saturation bounds as s16x2 pairs (PQ_FLAG_BIAS_FOLDED,
+    include/pq_sm100.h).  Returned unchanged when the fold does not apply (N % 16 != 0 or rs outside [1, 20])."""
     require_cuda(bias_i32, "bias_fold")
     n = bias_i32.numel()
-    if n % 4 or bias_i32.dtype != torch.int32 or not 1 <= int(rs) <= 20:
+    if n % 16 or bias_i32.dtype != torch.int32 or not 1 <= int(rs) <= 20:
         return bias_i32
-    out = torch.empty(2 * n, dtype=torch.int32, device=bias_i32.device)
+    out = torch.empty(3 * n, dtype=torch.int32, device=bias_i32.device)
     check(lib().pq_bias_fold_s32(bias_i32.contiguous().data_ptr(), n, int(rs), out.data_ptr(), _stream(bias_i32)),
           "pq_bias_fold_s32")
     return out
 
 
 def _bias_flags(bias_q, n, relu):
-    return (FLAG_RELU if relu else 0) | (FLAG_BIAS_FOLDED if bias_q.numel() == 2 * n else 0)
+    return (FLAG_RELU if relu else 0) | (FLAG_BIAS_FOLDED if bias_q.numel() == 3 * n else 0)
 
 
 def _flat_out(x):

@@ -310,6 +310,14 @@ __global__ void bias_fold_kernel(const int32_t *__restrict__ b, int n, int rs, i
     const int v = max(-128, min(127, b[i]));               // BiasAdd operands are int8-saturated (new_quantity_op.py:148)
     out[i] = v;
     out[n + i] = (rs >= 1 && rs <= 20) ? (1 << (rs - 1)) + v * (1 << rs) : 0;
+    // third row: the post-shift saturation bounds as s16x2 pairs of adjacent channels (see requant_packed16):
+    //   words [0, n/2): h = 127 + min(b, 0);   words [n/2, n): l = -128 + max(b, 0)
+    if ((i & 1) == 0 && i + 1 < n) {
+        const int v1 = max(-128, min(127, b[i + 1]));
+        const int h0 = 127 + min(v, 0), h1 = 127 + min(v1, 0), l0 = -128 + max(v, 0), l1 = -128 + max(v1, 0);
+        out[2 * n + (i >> 1)] = (int32_t)(((uint32_t)(uint16_t)(int16_t)h1 << 16) | (uint32_t)(uint16_t)(int16_t)h0);
+        out[2 * n + (n >> 1) + (i >> 1)] = (int32_t)(((uint32_t)(uint16_t)(int16_t)l1 << 16) | (uint32_t)(uint16_t)(int16_t)l0);
+    }
 }
 
 }  // namespace pq

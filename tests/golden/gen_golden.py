@@ -510,6 +510,37 @@ def gen_r18_224():
           % (res["seconds_activation_quantize"], res["seconds_weight_quantize"], wn))
 
 
+# ------------------------------------------------- per-channel max-abs, pinned by composition
+# name, shape, channel_dim, scale: activations [N][C][H][W], an FC activation [N][C], a conv weight per output channel
+CHANNEL_CASES = [("act_nchw", (3, 16, 9, 7), 1, 2.0), ("act_7x7", (4, 40, 7, 7), 1, 1.0), ("fc", (5, 24), 1, 3.0),
+                 ("weight_k", (12, 8, 3, 3), 0, 0.05)]
+
+
+def channel_batches(case):
+    name, shape, dim, scale = case
+    seed = 5000 + sum(ord(c) for c in name)
+    n = int(np.prod(shape))
+    return [det_inputs.bell(n, seed + i, scale * (1 + i)).reshape(shape) for i in range(2)]
+
+
+def gen_channel():
+    """The reference has no per-channel reduction, but its per-tensor one (refresh_max_val,
+    distribution_collector.py:70-78) applied to every channel slice AS A TENSOR OF ITS OWN is the per-channel
+    max-abs by definition: the unmodified reference collector is run on the slices (two batches, running max)."""
+    dc = ref_loader.load_l2("distribution_collector")
+    out = {}
+    for case in CHANNEL_CASES:
+        name, shape, dim, _ = case
+        C = shape[dim]
+        names = ["c%d" % c for c in range(C)]
+        col = dc.DistributionCollector(names)
+        for x in channel_batches(case):
+            col.refresh_max_val({"c%d" % c: np.ascontiguousarray(np.take(x, c, axis=dim)).reshape(-1) for c in range(C)})
+        out[name + "/max"] = np.array([col.max_vals[n] for n in names], dtype=np.float32)
+        print("channel", name, out[name + "/max"][:4])
+    _save("channel_max.npz", **out)
+
+
 # ------------------------------------------------------------ INTERVAL_NUM != 2048
 BINS_CASES = (512, 1000, 4096)
 
@@ -554,7 +585,7 @@ def gen_bins():
     _save("bins.npz", **out)
 
 
-SECTIONS = {"bins": gen_bins, "intsim_ext": gen_intsim_ext, "stats": gen_stats, "kl": gen_kl, "fakequant": gen_fakequant, "intsim": gen_intsim,
+SECTIONS = {"channel": gen_channel, "bins": gen_bins, "intsim_ext": gen_intsim_ext, "stats": gen_stats, "kl": gen_kl, "fakequant": gen_fakequant, "intsim": gen_intsim,
             "tiny": gen_tiny, "tiny_dkl": gen_tiny_dkl, "lenet": gen_lenet, "r18_224": gen_r18_224}
 
 if __name__ == "__main__":

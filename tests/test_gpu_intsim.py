@@ -199,7 +199,11 @@ def test_folded_bias_epilogue_equals_classic(oracle, M, N, K, rs, relu):
     bias[:4] = [-128, 127, 0, -1]
     ta, tw, tb = torch.from_numpy(a).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(bias).cuda()
     folded_bias = _native.bias_fold(tb, rs)
-    assert folded_bias.numel() == 2 * N and torch.equal(folded_bias[:N], tb)
+    assert folded_bias.numel() == 3 * N and torch.equal(folded_bias[:N], tb)
+    b64 = bias.astype(np.int64)
+    assert np.array_equal(folded_bias[N:2 * N].cpu().numpy().astype(np.int64), (1 << (rs - 1)) + (b64 << rs))
+    pairs = folded_bias[2 * N:].cpu().numpy().view(np.int16).astype(np.int64)       # [h pairs | l pairs], channel order
+    assert np.array_equal(pairs[:N], 127 + np.minimum(b64, 0)) and np.array_equal(pairs[N:], -128 + np.maximum(b64, 0))
     _, classic = _native.gemm_s8(ta, tw, tb, rs, 3, want_f32=False, want_s8=True, relu=relu)
     _, folded = _native.gemm_s8(ta, tw, folded_bias, rs, 3, want_f32=False, want_s8=True, relu=relu)
     assert torch.equal(classic, folded)

@@ -388,3 +388,16 @@ def test_interval_num_limits():
     assert lib.pq_kl_search_n_f64(c.data_ptr(), 1, 128, ws.data_ptr(), None, thr.data_ptr(), None) == -1    # PQ_EINVAL
     assert lib.pq_kl_search_n_f64(c.data_ptr(), 1, 8193, ws.data_ptr(), None, thr.data_ptr(), None) == -2   # PQ_EUNSUPPORTED
     assert lib.pq_hist_multi_f32(None, None, None, 0, 9000, None, None) == -2
+
+
+def test_per_channel_absmax_vs_reference_on_slices():
+    """pq_absmax_per_channel_f32 against channel_max.npz: the unmodified reference's per-tensor reduction
+    (distribution_collector.py:70-78) applied to every channel slice as a tensor of its own, two batches."""
+    from common.quantity import _native
+    g = load_golden("channel_max.npz")
+    for case in gg.CHANNEL_CASES:
+        name, shape, dim, _ = case
+        bits = torch.zeros(shape[dim], dtype=torch.int32, device="cuda")
+        for x in gg.channel_batches(case):
+            _native.absmax_per_channel(torch.from_numpy(x).cuda(), bits, dim)
+        assert np.array_equal(bits.view(torch.float32).cpu().numpy(), g[name + "/max"]), name

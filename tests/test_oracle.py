@@ -354,6 +354,13 @@ def test_folded_bias_identity(oracle):
         relu = np.clip(np.maximum(rha_plus_b(np.minimum(acc, a_hi)), 0), -128, 127)
         assert np.array_equal(relu, np.maximum(classic, 0)), rs
         assert np.abs(np.clip(acc, a_lo, a_hi) + c).max() < 2 ** 31
+        # round 2: both saturations BEHIND the shift as per-channel bounds on t = r + b (r NOT saturated), after a
+        # saturating pack to int16 (monotone; |l|, |h| <= 255): Sp(Sp(r) + b) == clamp(sat16(t), l, h)
+        t16 = np.clip(rha_plus_b(acc), -32768, 32767)
+        h, l = 127 + np.minimum(b, 0), -128 + np.maximum(b, 0)
+        assert np.array_equal(np.clip(t16, l, h), classic), rs
+        assert np.array_equal(np.maximum(np.minimum(t16, h), 0), np.maximum(classic, 0)), rs      # VIMNMX.S16x2.RELU
+        assert np.abs(acc + c).max() < 2 ** 31
 
 
 def test_c1_resnet18_reference_histograms(oracle):
@@ -393,3 +400,17 @@ def test_other_interval_num_vs_golden(oracle, nbins):
     np.testing.assert_allclose(kl, g[name + "/kl"], rtol=1e-12, atol=0)
     bit, thr = oracle.threshold_to_bit(t, iv)
     assert bit == int(g[name + "/bit"][0]) and float(thr) == float(g[name + "/threshold_value"][0])
+
+
+# ------------------------------------------- per-channel max-abs, pinned by composition (extension of a1)
+def test_per_channel_absmax_vs_reference_on_slices(oracle):
+    """channel_max.npz: the UNMODIFIED reference collector run on every channel slice as a tensor of its own (two
+    batches, running max) -- the per-channel max-abs by definition -- against the oracle's per-channel statement."""
+    from golden import gen_golden as gg
+    g = load_golden("channel_max.npz")
+    for case in gg.CHANNEL_CASES:
+        name, shape, dim, _ = case
+        cur = None
+        for x in gg.channel_batches(case):
+            cur = oracle.absmax_per_channel(x, dim, cur=cur)
+        assert cur.dtype == np.float32 and np.array_equal(cur, g[name + "/max"]), name
