@@ -183,9 +183,10 @@ int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias
  *   [2] N/2 words of s16x2 pairs (channels 2j, 2j+1)  h = 127 + min(bias, 0),  then N/2 words of pairs
  *       l = -128 + max(bias, 0)
  * The int8-only (staged) epilogue then folds BiasAdd (new_quantity_op.py:128-131) into the rounding add of
- * RightShift (:30-37),  t = (acc + [1] + (acc >> 31)) >> rs = round_half_away(acc / 2^rs) + bias,  and replaces both
- * saturations (:41, :71-91) by  clamp(t, l, h)  on packed 16-bit pairs -- the same integers (the composition
- * Sp(Sp(r) + b) is monotone in r and constant beyond the int8 range of r) with two ALU operations less per element.
+ * RightShift (:30-37),  t = (acc + [1] + (acc >> 31)) >> rs = round_half_away(acc / 2^rs) + bias,  with RightShift's
+ * saturation (:41) applied to the accumulator (channel-independent bounds) and the second one (:71-91) in the packing
+ * instruction; the fused-add epilogue instead replaces both saturations by  clamp(t, l, h)  on packed 16-bit pairs
+ * (the composition Sp(Sp(r) + b) is monotone in r and constant beyond the int8 range of r).  Same integers either way.
  * Ignored unless 1 <= rs <= 20 and N % 16 == 0. */
 #define PQ_FLAG_BIAS_FOLDED 2
 /* out: int32 [3 * n] (rows [0], [1], [2] above; n even). */

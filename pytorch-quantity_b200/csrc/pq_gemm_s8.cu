@@ -419,9 +419,10 @@ __device__ __forceinline__ int requant_folded(int acc, int sh, int a_lo, int a_h
 // l = -128 + max(b, 0): the function r -> Sp(Sp(r) + b) is monotone, equals r + b in between and is constant h
 // (l) above (below) the int8 range of r; under a fused ReLU l <= 0 is redundant.  Two accumulators are packed with
 // signed saturation (I2IP.S16.S32.SAT: monotone, and |l|, |h| <= 255), clamped as a pair (VIMNMX.S16x2[.RELU]) and
-// their low bytes gathered by one PRMT per four: 3.25 ALU-pipe operations per element with a ReLU (3.75 without)
-// instead of 4.5 (5.5) -- the pre-shift clamps on the 32-bit accumulator are gone.  h / l travel as s16x2 pairs in
-// the third row of the folded bias buffer (pq_bias_fold_s32): two LDG.128 per 16 channels, warp-uniform.
+// their low bytes gathered by one PRMT per four -- the pre-shift clamps on the 32-bit accumulator are gone.  h / l
+// travel as s16x2 pairs in the third row of the folded bias buffer (pq_bias_fold_s32): two LDG.128 each per 16
+// channels, warp-uniform.  Used by the fused-add epilogue (16 launches of ResNet-50: 2.85 -> 2.75 ms), NOT by the
+// plain int8 epilogue, where the extra loads cost more than the arithmetic saves (measured, see below).
 template <bool RELU>
 __device__ __forceinline__ void requant_packed16(const uint32_t (&a)[16], int sh, const int32_t *c_row,
                                                  const uint32_t *h_row, const uint32_t *l_row, uint32_t (&w)[8])
@@ -516,11 +517,19 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
                 // it); bias is 64-byte aligned: 4 x LDG.128, warp-uniform
                 if (n0 + c0 >= p.N) return;
                 if (FOLD != 0) {
-                    uint32_t w[8];
-                    const uint32_t *hrow = p.bias_hl + ((n0 + c0) >> 1);
-                    requant_packed16<FOLD == 2>(a, rq.sh, p.bias_c + n0 + c0, hrow, hrow + (p.N >> 1), w);
+                    // (the packed post-shift saturation of requant_packed16 was measured here too: no gain with a
+                    // fused ReLU, 4-10 % SLOWER without -- the two extra bound vectors cost more than the two ALU
+                    // operations they save; it pays only in the fused-add epilogue, whose tail is packed anyway)
+                    const int4 *cp = reinterpret_cast<const int4 *>(p.bias_c + n0 + c0);
+                    const int a_hi = 127 * (1 << rq.sh) + rq.half - 1, a_lo = -128 * (1 << rq.sh) - rq.half + 1;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) packed[j] = __byte_perm(w[2 * j], w[2 * j + 1], 0x6420);
+                    for (int j = 0; j < 4; ++j) {
+                        const int4 c4 = __ldg(cp + j);
+                        packed[j] = pack4_sat_s8(requant_folded<FOLD == 2>((int)a[4 * j], rq.sh, a_lo, a_hi, c4.x),
+                                                 requant_folded<FOLD == 2>((int)a[4 * j + 1], rq.sh, a_lo, a_hi, c4.y),
+                                                 requant_folded<FOLD == 2>((int)a[4 * j + 2], rq.sh, a_lo, a_hi, c4.z),
+                                                 requant_folded<FOLD == 2>((int)a[4 * j + 3], rq.sh, a_lo, a_hi, c4.w));
+                    }
                     return;
                 }
                 const int4 *bp = reinterpret_cast<const int4 *>(p.bias + n0 + c0);
