@@ -147,12 +147,14 @@ def peaks():
 
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
-    capture of this same bench command (profiles/r01_traffic.json, written by profiles/summarize.py)."""
-    try:
-        with open(os.path.join(REPO, "profiles", "r01_traffic.json")) as f:
-            return float(json.load(f)[kernel]["dram_bytes_per_launch"])
-    except (OSError, KeyError, ValueError):
-        return None
+    capture of this same bench command (profiles/rNN_traffic.json, written by profiles/summarize.py)."""
+    for tag in ("r02", "r01"):                     # the latest committed capture
+        try:
+            with open(os.path.join(REPO, "profiles", tag + "_traffic.json")) as f:
+                return float(json.load(f)[kernel]["dram_bytes_per_launch"])
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
 def fakequant_bandwidth(n_elems=1 << 28, iters=10):
@@ -296,7 +298,8 @@ def ours(args):
     extras = {}
     if not args.no_extras:
         t0 = time.perf_counter()
-        extras["c3_full"] = c3_full_job(net, workdir, rank, world)
+        for _ in range(int(os.environ.get("PQ_BENCH_C3_REPEAT", "1"))):
+            extras["c3_full"] = c3_full_job(net, workdir, rank, world)
         _note(t0, "c3_full")
         torch.cuda.empty_cache()
         if rank == 0 and world == 1:
@@ -350,6 +353,8 @@ def c3_full_job(net, workdir, rank, world, total_images=8192):
     pool = [make_batch(50_000 + rank * 16 + i, pin=True) for i in range(min(16, n_global // world))]
     secs, q = run_job(net, CycledBatches(pool, n_global, rank, world), n_global, workdir, rank, world)
     t = q.timings
+    print("[bench] c3_full rank %d: %s" % (rank, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in t.items()}),
+          file=sys.stderr, flush=True)
     return {"images": total_images, "steps_per_rank": t["batches"], "seconds": round(secs, 3),
             "images_per_s": round(total_images / secs, 1),
             "pass2_from_hbm_cache": t["cached_batches"], "pass2_forward_reruns": t["batches"] - t["cached_batches"],
