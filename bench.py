@@ -302,7 +302,7 @@ def ours(args):
             extras["c3_full"] = c3_full_job(net, workdir, rank, world)
         _note(t0, "c3_full")
         torch.cuda.empty_cache()
-        if rank == 0 and world == 1:
+        if rank == 0 and world == 1 and os.environ.get("PQ_BENCH_ONLY_C3") != "1":   # (development: c3_full only)
             extras.update(sim_extras(peak))
             t0 = time.perf_counter()
             extras["c1"] = c1_extra()
@@ -345,13 +345,45 @@ class CycledBatches:
             yield (self.pool[(i // self.world) % len(self.pool)], None) if i % self.world == self.rank else None
 
 
+def _alloc_stats(tag):
+    s = torch.cuda.memory_stats()
+    free, _total = torch.cuda.mem_get_info()
+    print("[bench] %s: reserved %.1f GB, allocated %.1f GB, device-free %.1f GB, segments %d, cudaMalloc calls %d, "
+          "allocator retries %d" % (tag, s["reserved_bytes.all.current"] / 1e9, s["allocated_bytes.all.current"] / 1e9,
+                                    free / 1e9, s["segment.all.current"], s["num_device_alloc"], s["num_alloc_retries"]),
+          file=sys.stderr, flush=True)
+
+
 def c3_full_job(net, workdir, rank, world, total_images=8192):
     """BASELINE config 3 at its stated size: 8192 images = 128 micro-batches of 64 shared by the ranks, host batches,
     through the public call.  At N = 1 the 550 GB of observed activations do not fit the HBM cache, so most of
     pass 2 re-runs the forward; from N = 4 on everything is served from the cache."""
     n_global = total_images // MICRO_BATCH
     pool = [make_batch(50_000 + rank * 16 + i, pin=True) for i in range(min(16, n_global // world))]
-    secs, q = run_job(net, CycledBatches(pool, n_global, rank, world), n_global, workdir, rank, world)
+    trace = os.environ.get("PQ_BENCH_C3_TRACE") == "1"          # per-batch device times of pass 1 + allocator statistics
+    if trace:
+        import common.quantity.distribution_collector as dc
+        events, orig = [], dc.DistributionCollector.refresh_max_val
+
+        def traced(self, feats):
+            r = orig(self, feats)
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            events.append(e)
+            return r
+        dc.DistributionCollector.refresh_max_val = traced
+        _alloc_stats("c3_full before")
+    try:
+        secs, q = run_job(net, CycledBatches(pool, n_global, rank, world), n_global, workdir, rank, world)
+    finally:
+        if trace:
+            dc.DistributionCollector.refresh_max_val = orig
+    if trace:
+        _alloc_stats("c3_full after")
+        ms = [events[i].elapsed_time(events[i + 1]) for i in range(len(events) - 1)]
+        for a in range(0, len(ms), 16):
+            print("[bench]   pass-1 batches %3d-%3d device ms: %s" % (a + 2, min(a + 17, len(ms) + 1),
+                  " ".join("%5.1f" % v for v in ms[a:a + 16])), file=sys.stderr, flush=True)
     t = q.timings
     print("[bench] c3_full rank %d: %s" % (rank, {k: (round(v, 3) if isinstance(v, float) else v) for k, v in t.items()}),
           file=sys.stderr, flush=True)
