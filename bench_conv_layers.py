@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--only", type=int, default=None, help="run only this row of the table (for ncu captures)")
     ap.add_argument("--fused-add", action="store_true", help="conv + NewAdd + ReLU in one kernel (int16 shortcut)")
     ap.add_argument("--classic-bias", action="store_true", help="plain int32 bias (no PQ_FLAG_BIAS_FOLDED constants)")
+    ap.add_argument("--no-windows", action="store_true", help="3x3 layers through the im2col-TMA path (PQ_FLAG_NO_WINDOWS)")
     args = ap.parse_args()
     B = args.batch
     tot_conv = tot_q = tot_ops = 0.0
@@ -84,7 +85,7 @@ def main():
             q = _native.quantize_nchw_to_nhwc_s8(x, 4, cpad)
             t_q = time_ms(lambda: _native.quantize_nchw_to_nhwc_s8(x, 4, cpad))
             t_c = time_ms(lambda: _native.conv2d_s8(q, wk, bias, (s, s), (pad, pad), 9, 4, want_f32=not args.s8_out,
-                                                    want_s8=args.s8_out))
+                                                    want_s8=args.s8_out, windows=not args.no_windows))
         ops = 2.0 * B * P * P * cout * k * k * cin
         out_bytes = B * P * P * cout * (1 if args.s8_out else 4)
         if args.fused_add and t_q == 0.0:             # all bytes of the fused kernel: A, shortcut int16, int16 + int8 out

@@ -189,6 +189,9 @@ int pq_conv2d_s8(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias
  * (the composition Sp(Sp(r) + b) is monotone in r and constant beyond the int8 range of r).  Same integers either way.
  * Ignored unless 1 <= rs <= 20 and N % 16 == 0. */
 #define PQ_FLAG_BIAS_FOLDED 2
+/* PQ_FLAG_NO_WINDOWS (pq_conv2d_s8_ex): take the im2col-TMA path even where the patch-window path applies (3x3,
+ * stride 1, pad 1, C = 64 / 128, one tile of output channels); both are bit-identical, the flag exists for A/B tests. */
+#define PQ_FLAG_NO_WINDOWS 4
 /* out: int32 [3 * n] (rows [0], [1], [2] above; n even). */
 int pq_bias_fold_s32(const int32_t *bias_q, int n, int rs, int32_t *out, pq_stream_t stream);
 int pq_gemm_s8_ex(const int8_t *a, const int8_t *w, const int32_t *bias_q, int M, int N, int K, int rs,

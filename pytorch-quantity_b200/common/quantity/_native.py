@@ -58,6 +58,7 @@ SYMBOLS = {
 }
 FLAG_RELU = 1
 FLAG_BIAS_FOLDED = 2
+FLAG_NO_WINDOWS = 4          # pq_conv2d_s8_ex: force the im2col-TMA path (A/B tests of the patch-window path)
 
 
 class ConvDesc(ctypes.Structure):
@@ -377,7 +378,7 @@ def gemm_s8(a, w, bias_q, rs, ob, hw=1, want_f32=True, want_s8=False, k_real=Non
 
 
 def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, want_s8=False, c_real=None,
-              relu=False, dilation=(1, 1)):
+              relu=False, dilation=(1, 1), windows=True):
     require_cuda(x_nhwc, "conv2d_s8")
     N, H, W, C = x_nhwc.shape
     K, R, S, C2 = w_krsc.shape
@@ -391,7 +392,8 @@ def conv2d_s8(x_nhwc, w_krsc, bias_q, stride, padding, rs, ob, want_f32=True, wa
     with _Timed("conv_s8", 1, 2 * N * P * Q * K * R * S * (c_real or C), x_nhwc.device):   # int8 ops
         if (dh, dw) == (1, 1):
             check(lib().pq_conv2d_s8_ex(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),
-                                        _bias_flags(bias_q, K, relu), out_f32.data_ptr() if want_f32 else None,
+                                        _bias_flags(bias_q, K, relu) | (0 if windows else FLAG_NO_WINDOWS),
+                                        out_f32.data_ptr() if want_f32 else None,
                                         out_s8.data_ptr() if want_s8 else None, _stream(x_nhwc)), "pq_conv2d_s8")
         else:
             check(lib().pq_conv2d_s8_dil(x_nhwc.data_ptr(), w_krsc.data_ptr(), bias_q.data_ptr(), ctypes.byref(d),

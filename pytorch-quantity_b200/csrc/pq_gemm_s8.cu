@@ -108,6 +108,14 @@ __device__ __forceinline__ void tma_load_3d_a(const CUtensorMap *map, uint32_t b
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_a(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                              int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_5d_a(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
                                               int c3, int c4)
 {
@@ -302,6 +310,13 @@ struct GemmParams {
     int16_t *out16;
     int tw_shift, TW, TH;      // output patch of one tile: TH x TW = 128 pixels, TW = 1 << tw_shift
     int tiles_p, tiles_q;      // patches per image
+    // a_im2col == 3, "patch windows" (3x3, stride 1, pad 1, C == BK, one n tile, resident weights): the A operand of
+    // a tile is ONE tiled TMA box [TH + 2 input rows][TW pixels from column -1][C] (hardware zero fill = the padding),
+    // and the nine taps are nine shared-memory descriptors into it: GEMM row i = pixel (i / TW, i % TW) of the patch
+    // reads box pixel i + r * TW + s, i.e. the same K-major rows C bytes apart, start address shifted by
+    // (r * TW + s) * C bytes.  Patch columns >= Q (at least two of the TW) read the neighbouring box row: those GEMM
+    // rows are junk and never stored.  L2 -> SM traffic per tile: (TH + 2) / TH input tiles instead of nine.
+    int win_slot_bytes, win_slots;
     const int32_t *bias;       // [N] quantised bias (already saturated to int8 range)
     const int32_t *bias_c;     // PQ_FLAG_BIAS_FOLDED (1 <= rs <= 20): [N] 2^(rs-1) + (bias << rs), see requant_folded
     const uint32_t *bias_hl;   // PQ_FLAG_BIAS_FOLDED: [N/2] s16x2 pairs 127 + min(b, 0), then [N/2] pairs -128 + max(b, 0)
@@ -481,7 +496,7 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
         const int m0 = (tile / n_tiles) * kBM, nt0 = (tile % n_tiles) * BN, n0 = nt0 + part * kCols;
         int m = m0 + row, p_img = 0, p_row = 0, p_col = 0;
         bool row_ok = m < p.M;
-        if (p.a_im2col == 2) {                     // tile row -> pixel of the TH x TW output patch
+        if (p.a_im2col >= 2) {                     // tile row -> pixel of the TH x TW output patch
             const int mt = tile / n_tiles, per_img = p.tiles_p * p.tiles_q;
             p_img = mt / per_img;
             const int rem = mt - p_img * per_img;
@@ -616,7 +631,7 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    if (p.a_im2col == 2) {         // 32 tile rows = a (32 / TW) x min(TW, 32) piece of the patch
+                    if (p.a_im2col >= 2) {         // 32 tile rows = a (32 / TW) x min(TW, 32) piece of the patch
                         const int r0 = quad * 32;
                         tma_store_4d(tmap_o, stage_buf, colb, p_col + (r0 & (p.TW - 1)), p_row + (r0 >> p.tw_shift), p_img);
                     } else {
@@ -981,6 +996,71 @@ __device__ __forceinline__ void produce_a(const GemmParams &p, const CUtensorMap
     }
 }
 
+// ---- a_im2col == 3 (patch windows, see GemmParams): one box per tile, nine descriptors per box
+template <int BK>
+__device__ __forceinline__ void produce_windows(const GemmParams &p, const CUtensorMap *tmap_a, uint8_t *smem_a,
+                                                uint64_t *full_bar, uint64_t *empty_bar, int total_tiles)
+{
+    const bool leader = elect_one();
+    const uint32_t a_base = smem_u32(smem_a), full_base = smem_u32(full_bar);
+    const uint32_t bytes = (uint32_t)((p.TH + 2) * p.TW * BK);
+    int slot = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {      // one n tile: tile == patch
+        const int img = tile / p.tiles_p, h0 = (tile - img * p.tiles_p) * p.TH;
+        mbar_wait(empty_bar + slot, phase ^ 1);
+        if (leader) {
+            const uint32_t bar = full_base + (uint32_t)slot * 8u;
+            mbar_expect_tx_a(bar, bytes);
+            tma_load_4d_a(tmap_a, bar, a_base + (uint32_t)(slot * p.win_slot_bytes), 0, -p.pad_w, h0 - p.pad_h, img);
+        }
+        __syncwarp();
+        if (++slot == p.win_slots) { slot = 0; phase ^= 1; }
+    }
+}
+
+template <int BN, int BK>
+__device__ __forceinline__ void mma_windows(const GemmParams &p, uint8_t *smem_a, uint8_t *smem_b, uint64_t *full_bar,
+                                            uint64_t *empty_bar, uint64_t *tmem_full_bar, uint64_t *tmem_empty_bar,
+                                            uint64_t *bres_bar, uint32_t tmem_base, int total_tiles, int kAcc)
+{
+    constexpr uint32_t idesc = make_idesc_i8(kBM, BN < 16 ? 16 : BN);
+    constexpr uint32_t kBBytes = BN * BK;
+    const bool leader = elect_one();
+    const uint64_t da0 = make_smem_desc<BK>(smem_u32(smem_a)), db0 = make_smem_desc<BK>(smem_u32(smem_b));
+    const uint32_t empty_base = smem_u32(empty_bar), tfull_base = smem_u32(tmem_full_bar);
+    const uint32_t row_step = (uint32_t)(p.TW * BK) >> 4;                 // one filter row down, in descriptor units
+    int slot = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    mbar_wait(bres_bar, 0);                                               // the weights: nine [BN][BK] tiles, tap-major
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
+        mbar_wait(full_bar + slot, phase);
+        tc_fence_after();
+        if (leader) {
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            uint64_t da_r = da0 + (uint64_t)((uint32_t)(slot * p.win_slot_bytes) >> 4);
+            uint64_t db = db0;
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const uint64_t da = da_r + (uint64_t)((uint32_t)(s * BK) >> 4);
+#pragma unroll
+                    for (int k = 0; k < BK / 32; ++k)
+                        umma_i8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (r | s | k) != 0);
+                    db += kBBytes >> 4;
+                }
+                da_r += row_step;
+            }
+            umma_commit_a(empty_base + (uint32_t)slot * 8u);
+            umma_commit_a(tfull_base + (uint32_t)acc * 8u);
+        }
+        __syncwarp();
+        if (++slot == p.win_slots) { slot = 0; phase ^= 1; }
+        if (++acc == kAcc) { acc = 0; acc_phase ^= 1; }
+    }
+}
+
 template <int BN, int BK, int STAGES, bool ADDK = false, int BSLOTS = STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)     // 19 warps = 5 on one SM sub-partition: <= 104 registers / thread
 gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -1006,7 +1086,7 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
     constexpr uint32_t kTmemCols = EpiCfg<BN, true>::kTmemCols;
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int total_tiles = (p.a_im2col == 2 ? p.M / kBM : (p.M + kBM - 1) / kBM) * n_tiles;   // mode 2: M = patches * 128
+    const int total_tiles = (p.a_im2col >= 2 ? p.M / kBM : (p.M + kBM - 1) / kBM) * n_tiles;   // modes 2, 3: M = patches * 128
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -1034,7 +1114,8 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // One warp per operand: a single warp's dependent uniform-datapath chain costs ~8 cycles per
         // instruction (ncu: ~50 instructions = 410 cycles per K block with both operands in one warp),
         // which bounded every layer whose K block holds less than ~400 cycles of tensor work.
-        if (p.a_im2col == 1) produce_a<1, BK, STAGES>(p, &tmap_a, smem_a, full_bar, empty_bar, total_tiles, n_tiles);
+        if (p.a_im2col == 3) { if (!ADDK) produce_windows<BK>(p, &tmap_a, smem_a, full_bar, empty_bar, total_tiles); }
+        else if (p.a_im2col == 1) produce_a<1, BK, STAGES>(p, &tmap_a, smem_a, full_bar, empty_bar, total_tiles, n_tiles);
         else if (p.a_im2col == 2) produce_a<2, BK, STAGES>(p, &tmap_a, smem_a, full_bar, empty_bar, total_tiles, n_tiles);
         else produce_a<0, BK, STAGES>(p, &tmap_a, smem_a, full_bar, empty_bar, total_tiles, n_tiles);
     } else if (warp == kWarpB) {
@@ -1073,6 +1154,9 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (++stage == nss) { stage = 0; phase ^= 1; }
             }
         }
+    } else if (warp == 1 && !ADDK && p.a_im2col == 3) {
+        mma_windows<BN, BK>(p, smem_a, smem_b, full_bar, empty_bar, tmem_full_bar, tmem_empty_bar, bres_bar, tmem_base,
+                            total_tiles, kAcc);
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp, leader lane issues) =====================
         constexpr uint32_t idesc = make_idesc_i8(kBM, BN < 16 ? 16 : BN);
@@ -1394,7 +1478,7 @@ int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, 
     if (p.out_s8 && !p.out_f32 && (p.N & 15) == 0 && (((uintptr_t)p.out_s8) & 15) == 0) {
         constexpr int kSlab = pq::EpiCfg<BN, true>::kSlab;     // each epilogue warp stores [32 rows][kSlab bytes] boxes
         int rc;
-        if (p.a_im2col == 2) {                     // NHWC output addressed by (channel, q, p, image): TH x TW patches
+        if (p.a_im2col >= 2) {                     // NHWC output addressed by (channel, q, p, image): TH x TW patches
             const cuuint64_t dims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.Q, (cuuint64_t)p.P,
                                         (cuuint64_t)(p.M / pq::kBM / (p.tiles_p * p.tiles_q))};
             const cuuint64_t strides[3] = {(cuuint64_t)p.N, (cuuint64_t)p.N * p.Q, (cuuint64_t)p.N * p.Q * p.P};
@@ -1630,6 +1714,41 @@ int conv_impl(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *bias_q,
     if (d.C & 31) return PQ_EUNSUPPORTED;                            // im2col path: channel blocks of >= 32
     int rc = load_driver_entry_points();
     if (rc != PQ_OK) return rc;
+    // 3x3 / stride 1 / pad 1 with one K block per tap and one n tile (ResNet: C = 64 at 56x56, C = 128 at 28x28): patch
+    // windows (GemmParams, a_im2col == 3).  The im2col gather re-reads every input byte nine times out of L2 and bounds
+    // these layers at ~9.5 TB/s of L2 -> SM traffic; the window box is read (TH + 2) / TH times.
+    if (!add && !(flags & PQ_FLAG_NO_WINDOWS) && d.R == 3 && d.S == 3 && d.stride_h == 1 && d.stride_w == 1 &&
+        d.pad_h == 1 && d.pad_w == 1 && dil_h == 1 && dil_w == 1 &&
+        ((d.C == 64 && d.K <= 64) || (d.C == 128 && d.K > 64 && d.K <= 128)) && d.W + 2 <= 64) {
+        const int tw_shift = d.W + 2 <= 16 ? 4 : (d.W + 2 <= 32 ? 5 : 6);
+        const int TW = 1 << tw_shift, TH = pq::kBM / TW;
+        const int slot = ((TH + 2) * TW * d.C + 1023) / 1024 * 1024;
+        const int a_region = d.C == 64 ? 18 * pq::kBM * 64 : 3 * pq::kBM * 128;       // the A ring of the configurations below
+        const int max_slots = d.C == 64 ? 18 : 3;                                      // (their mbarrier pairs)
+        int slots = a_region / slot;
+        if (slots > max_slots) slots = max_slots;
+        const long long patches = (long long)d.N * ((d.P + TH - 1) / TH);
+        if (slots >= 2 && patches * pq::kBM <= 0x7fffffffLL) {
+            CUtensorMap ta, tb;
+            const cuuint64_t adims[4] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
+            const cuuint64_t astr[3] = {(cuuint64_t)d.C, (cuuint64_t)d.W * d.C, (cuuint64_t)d.H * d.W * d.C};
+            const cuuint32_t abox[4] = {(cuuint32_t)d.C, (cuuint32_t)TW, (cuuint32_t)(TH + 2), 1};
+            if ((rc = encode_nd(&ta, x_nhwc, 4, adims, astr, abox, d.C)) != PQ_OK) return rc;
+            const uint64_t ktot = (uint64_t)9 * d.C;
+            if ((rc = encode_2d(&tb, w_krsc, ktot, d.K, ktot, d.C, d.C == 64 ? 64 : 128)) != PQ_OK) return rc;
+            pq::GemmParams p = {};
+            p.a_im2col = 3; p.N = d.K; p.M = (int)(patches * pq::kBM);
+            p.R = 3; p.S = 3; p.C = d.C; p.cblocks = 1; p.num_kb = 9; p.tps = 1;
+            p.P = d.P; p.Q = d.Q; p.stride_h = 1; p.stride_w = 1; p.pad_h = 1; p.pad_w = 1; p.dil_h = 1; p.dil_w = 1;
+            p.tw_shift = tw_shift; p.TW = TW; p.TH = TH; p.tiles_q = 1; p.tiles_p = (d.P + TH - 1) / TH;
+            p.win_slot_bytes = slot; p.win_slots = slots;
+            p.rs = d.rs; p.ob = d.ob; p.hw = d.P * d.Q; p.bias = bias_q; p.out_f32 = out_f32_nchw; p.out_s8 = out_s8_nhwc;
+            p.relu = flags & PQ_FLAG_RELU;
+            apply_bias_fold(p, bias_q, flags, d.K, d.rs);
+            return d.C == 64 ? launch_cfg<64, 64, 18, 9>(ta, tb, p, (cudaStream_t)stream)
+                             : launch_cfg<128, 128, 3, 9>(ta, tb, p, (cudaStream_t)stream);
+        }
+    }
     const int bk = (d.C % 128 == 0) ? 128 : ((d.C % 64 == 0) ? 64 : 32);
     int bn = pick_bn(M, d.K);
     if (add && bn < 64) bn = 64;                 // the fused-add pass works on 64-column slabs

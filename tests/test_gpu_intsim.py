@@ -277,3 +277,45 @@ def test_newconv2d_unsupported_padding_mode_is_a_named_error():
     conv = nn.Conv2d(16, 16, 3, padding=1, padding_mode="reflect").cuda()
     with pytest.raises(NotImplementedError, match="PQ_EUNSUPPORTED"):
         cq.NewConv2d(conv, {"weight_bit": 7, "input_bit": 4, "output_bit": 3, "bias_bit": 3})
+
+
+# Patch-window path (GemmParams a_im2col == 3): (B, C, H, W, K).  Covers every patch shape (2 x 64, 4 x 32, 8 x 16),
+# ragged last patches (H not a multiple of TH), the widest rows a patch takes (W + 2 == TW), fewer filters than the
+# tile holds and filter counts without the staged int8 store (K % 16 != 0).
+WINDOW_SHAPES = [(2, 64, 56, 56, 64), (3, 64, 28, 28, 48), (2, 64, 15, 30, 64), (2, 64, 9, 13, 32), (1, 64, 5, 62, 64),
+                 (2, 64, 3, 14, 24), (1, 64, 1, 1, 64), (2, 128, 28, 28, 128), (2, 128, 14, 14, 96), (1, 128, 7, 30, 128),
+                 (3, 128, 10, 9, 72), (2, 64, 33, 17, 64)]
+
+
+@pytest.mark.parametrize("shape", WINDOW_SHAPES, ids=["b%d_c%d_%dx%d_k%d" % s for s in WINDOW_SHAPES])
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("folded", [False, True])
+def test_conv_patch_windows_equal_im2col_and_exact_evaluation(shape, relu, folded):
+    """3x3 / stride 1 / pad 1 convolutions whose A operand is one TMA box per tile read through nine shifted
+    shared-memory descriptors: int8 NHWC and fp32 NCHW outputs must equal the im2col-TMA path bit for bit and an
+    independent evaluation (float64 convolution of the integer tensors + the integer epilogue of
+    new_quantity_op.py:11-44,124-133 in torch int64 ops)."""
+    from common.quantity import _native
+    B, C, H, W, K = shape
+    g = torch.Generator().manual_seed(B * 1000 + C + H * 7 + W * 13 + K)
+    x = torch.randint(-128, 128, (B, H, W, C), dtype=torch.int8, generator=g).cuda()
+    w = torch.randint(-128, 128, (K, 3, 3, C), dtype=torch.int8, generator=g).cuda()
+    bias = torch.randint(-128, 128, (K,), dtype=torch.int32, generator=g).cuda()
+    rs, ob = 11, 4
+    bq = _native.bias_fold(bias, rs) if folded and K % 16 == 0 else bias
+    outs = {}
+    for windows in (True, False):
+        f32, _ = _native.conv2d_s8(x, w, bq, (1, 1), (1, 1), rs, ob, want_f32=True, want_s8=False, relu=relu,
+                                   windows=windows)
+        _, s8 = _native.conv2d_s8(x, w, bq, (1, 1), (1, 1), rs, ob, want_f32=False, want_s8=True, relu=relu,
+                                  windows=windows)
+        outs[windows] = (f32, s8)
+    assert torch.equal(outs[True][1], outs[False][1])
+    assert torch.equal(outs[True][0], outs[False][0])
+    acc = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), padding=1).long()
+    r = torch.where(acc >= 0, (acc + (1 << (rs - 1))) >> rs, -((-acc + (1 << (rs - 1))) >> rs)).clamp(-128, 127)
+    y = (r + bias.long().view(1, K, 1, 1)).clamp(-128, 127)
+    if relu:
+        y = y.clamp(min=0)
+    assert torch.equal(outs[True][1].permute(0, 3, 1, 2).long(), y)
+    assert torch.equal(outs[True][0], y.float() / 16.0)
