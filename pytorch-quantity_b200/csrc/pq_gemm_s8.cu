@@ -750,25 +750,27 @@ __device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensor
             if (n0_of(t) < p.N) return it;
         }
     };
-    auto issue_load = [&](int buf, int tile, int slab) {     // leader lane only
-        const int m0r = (tile / n_tiles) * kBM + quad * 32, colb = n0_of(tile) + slab * kAddSlab;
+    // (row, column) of a slab are passed in: the tile -> coordinate divisions are done once per TILE, not per slab
+    // (ncu source view: a MUFU.RCP division sequence per slab, ~10 % of the epilogue's instructions)
+    auto issue_load = [&](int buf, int m0r, int colb) {      // leader lane only
         const uint32_t bar = bar_base + 8u * (uint32_t)buf;
         mbar_expect_tx_a(bar, sc_bytes);
         tma_load_2d_a(tmap_sc, bar, s16_base + (uint32_t)buf * kAddS16Bytes, sc16 ? colb * 2 : colb, m0r);
     };
+    auto row0_of = [&](int tile) { return (n_tiles == 1 ? tile : tile / n_tiles) * kBM + quad * 32; };
 
     uint32_t ph0 = 0u, ph1 = 0u;                       // parity of the next completion of either buffer's barrier
     int cur = 0;                                       // buffer that holds (or will hold) the current slab's shortcut
     {
         const int it0 = next_loaded_it(group);
-        if (it0 >= 0 && lane == 0) issue_load(0, tile_of(it0), 0);
+        if (it0 >= 0 && lane == 0) issue_load(0, row0_of(tile_of(it0)), n0_of(tile_of(it0)));
     }
     for (int it = group;; it += E::kGroups) {
         const int tile = tile_of(it);
         if (tile >= total_tiles) break;
         const int acc = it & (E::kAcc - 1);
         const uint32_t acc_phase = (uint32_t)(it / E::kAcc) & 1u;
-        const int m0r = (tile / n_tiles) * kBM + quad * 32, n0 = n0_of(tile);
+        const int m0r = row0_of(tile), n0 = n0_of(tile);
         int nslab = (p.N - n0 + kAddSlab - 1) / kAddSlab;             // slabs of this warp inside N
         nslab = nslab < 0 ? 0 : (nslab > kSlabs ? kSlabs : nslab);
         mbar_wait(tmem_full_bar + acc, acc_phase);
@@ -873,13 +875,14 @@ __device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensor
             if (lane == 0) bulk_wait_read0();
             __syncwarp();
             {                                          // prefetch the next slab's shortcut into the other buffer
-                int nt = tile, ns = slab + 1;
-                if (ns == nslab) {
+                int nrow = m0r, ncol = colb + kAddSlab;
+                bool more = true;
+                if (slab + 1 == nslab) {               // the first slab of this warp's next tile (divisions: once per tile)
                     const int itn = next_loaded_it(it + E::kGroups);
-                    nt = itn < 0 ? -1 : tile_of(itn);
-                    ns = 0;
+                    more = itn >= 0;
+                    if (more) { nrow = row0_of(tile_of(itn)); ncol = n0_of(tile_of(itn)); }
                 }
-                if (nt >= 0 && lane == 0) issue_load(cur ^ 1, nt, ns);
+                if (more && lane == 0) issue_load(cur ^ 1, nrow, ncol);
             }
             if (p.add_sc_relu) {                       // a pending nn.ReLU on the shortcut operand
 #pragma unroll
