@@ -177,6 +177,55 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void 
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+// variants on shared-window addresses + a value the optimiser cannot re-derive: under register pressure ptxas
+// rematerialises shared addresses (S2UR SR_CgaCtaId / SR_SWINHI, the 1024-byte alignment of the dynamic segment: ~20
+// instructions each time) and the lane id (S2R + its ~20-cycle latency) at every use inside the epilogue's slab
+// loop -- 150 of ~550 instructions per slab in the fused-add epilogue (ncu source view).
+__device__ __forceinline__ uint32_t keep_u32(uint32_t x)
+{
+    uint32_t y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_a(const CUtensorMap *map, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_a(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync(int threads)
@@ -475,7 +524,7 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
                                          int total_tiles, int n_tiles)
 {
     using E = EpiCfg<BN, FAST>;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (int)keep_u32(threadIdx.x >> 5), lane = (int)keep_u32(threadIdx.x & 31);   // (see keep_u32)
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
     const int idx = (warp - 2) >> 2;               // 0..3
     const int group = idx / E::kColSplit;          // which tiles (and which accumulator stage) this warp serves
@@ -483,7 +532,8 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
     constexpr int kCols = E::kCols, kSlab = E::kSlab;
     constexpr int kChunksPerSlab = kSlab / 16, kSlabs = kCols / kSlab;
     constexpr uint32_t kSwzMask = kSlab == 64 ? 3u : 1u;
-    uint8_t *stage_buf = smem_o + (warp - 2) * E::kSlabBytes;
+    const uint32_t stage_addr = keep_u32(smem_u32(smem_o + (warp - 2) * E::kSlabBytes));
+    const uint32_t tfull_base = keep_u32(smem_u32(tmem_full_bar)), tempty_base = tfull_base + 32u;   // [4] + [4] mbarriers
     const int row = quad * 32 + lane;
     const Requant rq = make_requant(p.rs, p.relu);
     const float dq = __int_as_float((127 - p.ob) << 23);        // 2^-ob, exact
@@ -521,7 +571,7 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
             }
             if (p.out_s8) o8 = p.out_s8 + (size_t)m * p.N + n0;     // generic path: direct int8 stores
         }
-        mbar_wait(tmem_full_bar + acc, acc_phase);
+        mbar_wait_a(tfull_base + 8u * (uint32_t)acc, acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kCols);
 
@@ -612,7 +662,7 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
                     // every TMEM read of this accumulator has completed: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+                    if (lane == 0) mbar_arrive_a(tempty_base + 8u * (uint32_t)acc);
                 }
                 if (j & 1) emit(a1, ch * 16, packed[j]);
                 else emit(a0, ch * 16, packed[j]);
@@ -625,17 +675,17 @@ __device__ __forceinline__ void epilogue(const GemmParams &p, const CUtensorMap 
 #pragma unroll
                 for (int j = 0; j < kChunksPerSlab; ++j) {
                     const uint32_t o = (uint32_t)(lane * kSlab + 16 * j);
-                    *reinterpret_cast<uint4 *>(stage_buf + (o ^ (((o >> 7) & kSwzMask) << 4))) =
-                        make_uint4(packed[j][0], packed[j][1], packed[j][2], packed[j][3]);
+                    sts_u4(stage_addr + (o ^ (((o >> 7) & kSwzMask) << 4)), packed[j][0], packed[j][1], packed[j][2],
+                           packed[j][3]);
                 }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
                     if (p.a_im2col >= 2) {         // 32 tile rows = a (32 / TW) x min(TW, 32) piece of the patch
                         const int r0 = quad * 32;
-                        tma_store_4d(tmap_o, stage_buf, colb, p_col + (r0 & (p.TW - 1)), p_row + (r0 >> p.tw_shift), p_img);
+                        tma_store_4d_a(tmap_o, stage_addr, colb, p_col + (r0 & (p.TW - 1)), p_row + (r0 >> p.tw_shift), p_img);
                     } else {
-                        tma_store_2d(tmap_o, stage_buf, colb, m0 + quad * 32);
+                        tma_store_2d_a(tmap_o, stage_addr, colb, m0 + quad * 32);
                     }
                     bulk_commit();
                 }
@@ -665,16 +715,6 @@ __device__ __forceinline__ uint32_t pack2_sat_s16(int hi, int lo)
     uint32_t d;
     asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
     return d;
-}
-__device__ __forceinline__ uint4 lds_u4(uint32_t addr)
-{
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 
@@ -717,15 +757,16 @@ __device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensor
                                              int total_tiles, int n_tiles)
 {
     using E = EpiCfg<BN, true>;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (int)keep_u32(threadIdx.x >> 5), lane = (int)keep_u32(threadIdx.x & 31);
     const int quad = warp & 3;
     const int idx = (warp - 2) >> 2;
     const int group = idx / E::kColSplit;
     const int part = idx % E::kColSplit;
     constexpr int kCols = E::kCols, kSlabs = kCols / kAddSlab;
-    const uint32_t wbase = smem_u32(smem_o + (warp - 2) * kAddWarpBytes);
+    const uint32_t wbase = keep_u32(smem_u32(smem_o + (warp - 2) * kAddWarpBytes));
     const uint32_t o8_base = wbase, s16_base = wbase + kAddO8Bytes;
-    const uint32_t bar_base = smem_u32(sc_bar_all + 2 * (warp - 2));
+    const uint32_t bar_base = keep_u32(smem_u32(sc_bar_all + 2 * (warp - 2)));
+    const uint32_t tfull_base = keep_u32(smem_u32(tmem_full_bar)), tempty_base = tfull_base + 32u;   // [4] + [4] mbarriers
     const Requant rq = make_requant(p.rs, 0);
     const bool sc16 = p.add_is16 != 0;
     const uint32_t sc_bytes = sc16 ? (uint32_t)kAddS16Bytes : (uint32_t)kAddO8Bytes;
@@ -773,13 +814,13 @@ __device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensor
         const int m0r = row0_of(tile), n0 = n0_of(tile);
         int nslab = (p.N - n0 + kAddSlab - 1) / kAddSlab;             // slabs of this warp inside N
         nslab = nslab < 0 ? 0 : (nslab > kSlabs ? kSlabs : nslab);
-        mbar_wait(tmem_full_bar + acc, acc_phase);
+        mbar_wait_a(tfull_base + 8u * (uint32_t)acc, acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + part * kCols);
         if (nslab == 0) {                              // nothing to do here, but the accumulator must be released
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+            if (lane == 0) mbar_arrive_a(tempty_base + 8u * (uint32_t)acc);
             continue;
         }
         uint32_t a0[16], a1[16];
@@ -798,7 +839,7 @@ __device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensor
                 } else {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+                    if (lane == 0) mbar_arrive_a(tempty_base + 8u * (uint32_t)acc);
                 }
                 const uint32_t (&a)[16] = (j & 1) ? a1 : a0;
                 if (colb + 16 * j < p.N) {
@@ -848,7 +889,7 @@ __device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensor
             }
             // ---- the shortcut of this slab has been on its way since the previous slab
             const uint32_t sbuf = s16_base + (uint32_t)cur * kAddS16Bytes;
-            mbar_wait(sc_bar_all + 2 * (warp - 2) + cur, cur ? ph1 : ph0);
+            mbar_wait_a(bar_base + 8u * (uint32_t)cur, cur ? ph1 : ph0);
             if (cur) ph1 ^= 1u; else ph0 ^= 1u;
             uint32_t sc[2][8];
             if (sc16) {
@@ -919,10 +960,8 @@ __device__ __forceinline__ void epilogue_add(const GemmParams &p, const CUtensor
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                tma_store_2d(tmap_o, reinterpret_cast<const void *>(smem_o + (warp - 2) * kAddWarpBytes), colb, m0r);
-                if (p.out16)
-                    tma_store_2d(tmap_o16, reinterpret_cast<const void *>(smem_o + (warp - 2) * kAddWarpBytes + kAddO8Bytes +
-                                                                          cur * kAddS16Bytes), colb * 2, m0r);
+                tma_store_2d_a(tmap_o, o8_base, colb, m0r);
+                if (p.out16) tma_store_2d_a(tmap_o16, sbuf, colb * 2, m0r);
                 bulk_commit();
             }
             cur ^= 1;
