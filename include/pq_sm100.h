@@ -214,6 +214,14 @@ int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const int32_t *b
                         const pq_conv_desc *desc_host, int Hp, int Wp, int flags, float *out_f32_nchw,
                         int8_t *out_s8_nhwc, pq_stream_t stream);
 
+/* Global average pool of a quantised NHWC payload (int8, or the int16 exact sum of a NewAdd) at fractional bit `bit`,
+ * with an optional pending ReLU: out[N][C] fp32 = nn.AvgPool2d(H)(DeQuantity(x)) bit for bit -- the fp32 window sum of
+ * the reference is exact while HW * max|x| < 2^24 (otherwise PQ_EUNSUPPORTED), then one IEEE division by HW as in
+ * ATen's avg_pool2d.  The pipeline's replacement for de-quantise + F.avg_pool2d (quantity/model/resnet: AvgPool2d ->
+ * View -> NewLinear).  C % 8 == 0. */
+int pq_avgpool_global_nhwc_f32(const void *x, int is16, int bit, int relu, int N, int HW, int C, float *out,
+                               pq_stream_t stream);
+
 /* y = max(x, 0) on int8 (nn.ReLU on a quantised tensor: relu commutes with the input quantiser). */
 int pq_relu_s8(const int8_t *x, int8_t *y, size_t n, pq_stream_t stream);
 

@@ -51,6 +51,7 @@ SYMBOLS = {
     "pq_conv2d_s8_add_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "pq_relu_s8": (_i, [_vp, _vp, _sz, _vp]),
     "pq_maxpool_nhwc_s8": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "pq_avgpool_global_nhwc_f32": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "pq_add_requant": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _sz, _vp, _vp, _i, _vp]),
     "pq_add_requant_ex": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _sz, _i, _vp, _vp, _i, _vp]),
     "pq_concat_requant_s8": (_i, [_vp, _i, _sz, _i, _i, _vp, _vp]),
@@ -446,6 +447,21 @@ def maxpool_nhwc_s8(x, k, stride, pad, relu=False):
     with _Timed("maxpool_s8", 1, x.numel() + y.numel(), x.device):
         check(lib().pq_maxpool_nhwc_s8(x.data_ptr(), y.data_ptr(), N, H, W, C, k, stride, pad, 1 if relu else 0,
                                        _stream(x)), "pq_maxpool_nhwc_s8")
+    return y
+
+
+def avgpool_global_nhwc(x, bit, relu=False):
+    """int8 / int16 NHWC payload at fractional bit `bit` -> fp32 [N][C][1][1] = AvgPool2d over the whole plane of the
+    de-quantised tensor (None when the exactness condition of pq_avgpool_global_nhwc_f32 does not hold)."""
+    require_cuda(x, "avgpool_global_nhwc")
+    N, H, W, C = x.shape
+    is16 = x.dtype == torch.int16
+    if C % 8 or H * W * (32768 if is16 else 128) >= (1 << 24) or not x.is_contiguous():
+        return None
+    y = torch.empty((N, C, 1, 1), dtype=torch.float32, device=x.device)
+    with _Timed("avgpool_s8", 1, x.numel() * x.element_size() + y.numel() * 4, x.device):
+        check(lib().pq_avgpool_global_nhwc_f32(x.data_ptr(), 1 if is16 else 0, int(bit), 1 if relu else 0, N, H * W, C,
+                                               y.data_ptr(), _stream(x)), "pq_avgpool_global_nhwc_f32")
     return y
 
 

@@ -258,6 +258,10 @@ class QTensor(torch.Tensor):
             out = _maxpool(args[0], *args[1:], **kwargs)
             if out is not None:
                 return out
+        if func is F.avg_pool2d and isinstance(args[0], QTensor):
+            out = _avgpool(args[0], *args[1:], **kwargs)
+            if out is not None:
+                return out
         # metadata queries are answered by the wrapper itself (no payload is touched)
         if getattr(func, "__name__", "") in _METADATA:
             with torch._C.DisableTorchFunctionSubclass():
@@ -312,6 +316,26 @@ def _maxpool(x, kernel_size, stride=None, padding=0, dilation=1, ceil_mode=False
     y = _native.maxpool_nhwc_s8(q8, k[0], s[0], p[0], relu=relu)
     N, P, Q, C = y.shape
     return QTensor((N, x.shape[1], P, Q), x.device, q8=y, q8_bit=x.q8_bit, nonneg=x.nonneg or relu)
+
+
+def _avgpool(x, kernel_size, stride=None, padding=0, ceil_mode=False, count_include_pad=True, divisor_override=None):
+    """F.avg_pool2d over the WHOLE plane (ResNet's AvgPool2d before the classifier) straight from the most exact
+    payload: fp32 [N][C][1][1], bit-identical to pooling the de-quantised tensor (pq_avgpool_global_nhwc_f32)."""
+    k = _pair(kernel_size)
+    if k != (x.shape[2], x.shape[3]) or _pair(padding) != (0, 0) or divisor_override is not None:
+        return None
+    if x._lazy_cat is not None or x.channels % 8:
+        return None
+    relu = x.relu_pending                          # (read before a lazy producer consumes it)
+    if x.s16_bit is not None:
+        payload, bit = x.s16, x.s16_bit
+    elif x.has_q8():
+        payload, bit = x.q8, x.q8_bit
+    else:
+        return None
+    if payload.shape[3] != x.channels:             # padded payload channels
+        return None
+    return _native.avgpool_global_nhwc(payload, bit, relu=relu and not x.nonneg)
 
 
 def conv_forward(mod, x):

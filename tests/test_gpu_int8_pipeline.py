@@ -313,3 +313,23 @@ def test_pipeline_add_writes_only_consumed_payloads(tmp_path):
     q8_only = [n for n, k in kinds.items() if k == frozenset({"q8"})]
     assert len(q8_only) == 3, kinds                                  # the last block of stages 1-3
     assert sum(1 for k in kinds.values() if k == both) == 4, kinds  # blocks followed by an identity shortcut
+
+
+@pytest.mark.parametrize("shape", [(4, 7, 7, 2048), (3, 7, 7, 64), (2, 14, 14, 24), (2, 1, 1, 8), (5, 4, 4, 512), (2, 16, 16, 40)])
+@pytest.mark.parametrize("is16", [False, True])
+@pytest.mark.parametrize("relu", [False, True])
+def test_avgpool_global_equals_torch_on_dequantised_tensor(shape, is16, relu):
+    """pq_avgpool_global_nhwc_f32 (the pipeline's AvgPool2d before the classifier) against F.avg_pool2d of the
+    de-quantised fp32 NCHW tensor, as the fp32-boundary model computes it: bit-identical."""
+    from common.quantity import _native
+    N, H, W, C = shape
+    g = torch.Generator().manual_seed(N * 100 + C + (7 if is16 else 0))
+    lim = 16384 if is16 else 128
+    q = torch.randint(-lim, lim, shape, generator=g, dtype=torch.int16 if is16 else torch.int8).cuda()
+    for bit in (6, 0, -2, 11):
+        y = _native.avgpool_global_nhwc(q, bit, relu=relu)
+        v = q.to(torch.float32) * (2.0 ** -bit)
+        if relu:
+            v = torch.relu(v)
+        ref = torch.nn.functional.avg_pool2d(v.permute(0, 3, 1, 2).contiguous(), (H, W))
+        assert y.shape == ref.shape and torch.equal(y, ref)
