@@ -44,6 +44,24 @@ maxpool_nhwc_s8_kernel(const int8_t *__restrict__ x, int8_t *__restrict__ y, int
     const int dq = kPipeThreads / cv, dc = kPipeThreads - dq * cv;   // advance of (q, c16) per loop trip
     for (int t = threadIdx.x; t < items; t += kPipeThreads) {
         uint4 m = make_uint4(init, init, init, init);
+        if (k == 3) {                              // the usual window: all nine loads in flight, out-of-range taps = init
+            uint4 v[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int iy = pp * stride - pad + r;
+                const int8_t *row = xin + (size_t)iy * W * C + c16 * 16;
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const int ix = q * stride - pad + s;
+                    v[3 * r + s] = ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
+                                       ? __ldg(reinterpret_cast<const uint4 *>(row + (size_t)ix * C)) : m;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                m.x = __vmaxs4(m.x, v[i].x); m.y = __vmaxs4(m.y, v[i].y); m.z = __vmaxs4(m.z, v[i].z); m.w = __vmaxs4(m.w, v[i].w);
+            }
+        } else
         for (int r = 0; r < k; ++r) {
             const int iy = pp * stride - pad + r;
             if ((unsigned)iy >= (unsigned)H) continue;
