@@ -50,9 +50,11 @@ def test_no_cpu_fallback_without_cuda():
 def test_json_writer_is_byte_identical_to_json_dump():
     from tools._jsonio import dumps_int_array
     rng = np.random.default_rng(0)
-    for shape in [(5,), (3, 4), (2, 3, 3, 3), (4, 1, 1, 1), (1,), (2, 0), (7, 2, 1)]:
-        a = rng.integers(-128, 128, size=shape).astype(np.int32)
-        assert dumps_int_array(a) == json.dumps(a.tolist(), indent=4), shape
+    for shape in [(5,), (3, 4), (2, 3, 3, 3), (4, 1, 1, 1), (1,), (2, 0), (7, 2, 1), (1, 1, 1, 1), (40,), (3, 40), (2, 3, 40),
+                  (64, 3, 7, 7), (5, 33), (33, 5), (2, 17, 2), (9, 2, 2, 2, 2), (2, 70000), (16, 8, 3, 3)]:
+        for lo, hi in ((-128, 128), (-99999, 100000), (0, 1), (-40000, 40000), (-3000000, 3000000)):
+            a = rng.integers(lo, hi, size=shape).astype(np.int32)        # (beyond 5 digits: the plain path)
+            assert dumps_int_array(a) == json.dumps(a.tolist(), indent=4), (shape, lo)
     a8 = rng.integers(-128, 128, size=(3, 2)).astype(np.int8)
     assert dumps_int_array(a8) == json.dumps(a8.tolist(), indent=4)
 
