@@ -651,7 +651,12 @@ def reference_arm(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": W,
             "ms_per_step": round(secs * 1e3 / K, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_images_per_step": per_step,
+            # the same keys as the GPU arm's config, with this arm's truthful values: the same workload, a bounded
+            # sample of it per step (2 images instead of 64) -- rates are per image
+            "config": {"workload": WORKLOAD, "global_batch": per_step, "images": n, "observed_tensors": 71,
+                       "elements_per_image": 16784872,
+                       "l2": "host memory (the reference copies every activation to numpy)",
+                       "pass2": "every step re-runs the forward (reference :415-426)", "parallelism": "cpu%d" % workers,
                        "job": "one whole activation_quantize job of %d batches (both passes + KL search of 71 tensors)" % K},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference",
                              "sample": "unmodified reference (baseline/_ref), DEVICE: cpu, WORKER_NUM %d: %d steps of %d "
