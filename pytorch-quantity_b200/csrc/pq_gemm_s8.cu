@@ -20,6 +20,7 @@
 // A STAGES-deep smem ring (full/empty mbarriers) decouples TMA from MMA; the two TMEM accumulators
 // (tmem_full/tmem_empty mbarriers) let the epilogue of tile i overlap the main loop of tile i+1.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "pq_common.cuh"
 
@@ -226,6 +227,13 @@ __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, ui
 {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// Programmatic dependent launch: every kernel here is launched with programmaticStreamSerializationAllowed, lets its
+// successor start as soon as this grid's CTAs have been scheduled (launch_dependents) and touches global memory only
+// after its predecessor has completed and flushed (wait).  A CTA of the next kernel lands on an SM as soon as this
+// kernel's CTA there has exited (one CTA per SM: shared memory), so its barrier / TMEM / tensor-map set-up overlaps the
+// tail of this kernel instead of following the launch latency.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync(int threads)
@@ -1150,6 +1158,8 @@ gemm_s8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_launch_dependents();
+    pdl_wait();                                        // operands / shortcut come from the preceding kernel
 
     if (warp == 0) {
         // ===================== A-operand TMA producer (whole warp, leader lane issues) =====================
@@ -1323,6 +1333,8 @@ conv_rows_s8_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_launch_dependents();
+    pdl_wait();
 
     // Both loops below run on the whole warp with the asynchronous instructions predicated on one leader
     // lane, and walk the tiles incrementally (no per-tile division): the single-lane version spent ~390
@@ -1499,6 +1511,22 @@ int num_sms()
     return n;
 }
 
+// cudaLaunchKernelEx with programmatic stream serialisation (see pdl_wait); PQ_NO_PDL=1 in the environment turns the
+// attribute off (the kernels' griddepcontrol instructions are then no-ops)
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kern)(KArgs...), int grid, size_t smem, cudaStream_t s, Args &&...args)
+{
+    static const bool no_pdl = [] { const char *e = getenv("PQ_NO_PDL"); return e && e[0] == '1'; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)pq::kGemmThreads);
+    cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    return (int)cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int BN, int BK, int STAGES, int BSLOTS = STAGES>
 int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, cudaStream_t s)
 {
@@ -1534,8 +1562,7 @@ int launch_cfg(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams &p, 
         p.stage_s8 = 1;
     }
     const CUtensorMap none = {};
-    kern<<<grid, pq::kGemmThreads, Cfg::kTotal, s>>>(ta, tb, to, none, none, p);
-    return (int)cudaGetLastError();
+    return launch_pdl(kern, grid, Cfg::kTotal, s, ta, tb, to, none, none, p);
 }
 
 // fused NewConv2d + NewAdd kernels (ADDK): int8 result, shortcut and int16 sum travel as [32 rows][32 channels]
@@ -1563,8 +1590,7 @@ int launch_cfg_add(const CUtensorMap &ta, const CUtensorMap &tb, pq::GemmParams 
     if (rc != PQ_OK) return rc;
     if (p.out16 && (rc = encode_2d(&to16, p.out16, 2 * N, M, 2 * N, 2 * pq::kAddSlab, 32)) != PQ_OK) return rc;
     p.stage_s8 = 1;
-    kern<<<grid, pq::kGemmThreads, Cfg::kTotal, s>>>(ta, tb, to, tsc, to16, p);
-    return (int)cudaGetLastError();
+    return launch_pdl(kern, grid, Cfg::kTotal, s, ta, tb, to, tsc, to16, p);
 }
 
 // stage counts: fill ~192 KB of shared memory, at most 8 stages
@@ -1894,8 +1920,7 @@ extern "C" int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const
             }
             const long long tiles = tiles_m * n_tiles;
             const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-            pq::conv_rows_s8_kernel<<<grid, pq::kGemmThreads, smem, (cudaStream_t)stream>>>(tb, to, q, rp);
-            return (int)cudaGetLastError();
+            return launch_pdl(pq::conv_rows_s8_kernel, grid, smem, (cudaStream_t)stream, tb, to, q, rp);
         }
     }
     // A: (byte in window, output column, row group, row phase, image); the column step overlaps the windows
