@@ -527,7 +527,7 @@ class Quantity(object):
             for name in names:                                               # (:650-653)
                 bits_co[name] = int(8 - 1 - math.ceil(math.log(max_vals[name], 2)))
 
-        table = []
+        table, writes = [], []
         for name in names:
             bit = bits_co[name]
             q = _native.fakequant(params[name], bit, -128.0, 127.0, dequant=False)   # around + clip
@@ -536,11 +536,23 @@ class Quantity(object):
                 continue
             content = q.to(torch.int32).view(shapes[name]).cpu().numpy()
             if name.endswith("weight"):
-                dump_int_array(content, os.path.join(out["WEIGHT_DIR"], name + ".json"))
+                writes.append((content, os.path.join(out["WEIGHT_DIR"], name + ".json")))
             elif name.endswith("bias"):
-                dump_int_array(content, os.path.join(out["BIAS_DIR"], name + ".json"))
+                writes.append((content, os.path.join(out["BIAS_DIR"], name + ".json")))
             else:
                 raise NotImplementedError(name)
+        if writes:
+            # the files are independent and the writer is numpy (the GIL is released in its large array operations):
+            # a few host threads, largest tensors first
+            writes.sort(key=lambda w: -w[0].size)
+            workers = max(1, min(8, os.cpu_count() or 1, len(writes)))
+            if workers == 1:
+                for content, path in writes:
+                    dump_int_array(content, path)
+            else:
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(workers) as pool:
+                    list(pool.map(lambda w: dump_int_array(*w), writes))
         if self.rank == 0:
             with open(out["WEIGHT_BIT_TABLE"], "w") as f:
                 for line in table:
