@@ -19,6 +19,9 @@
 //              (the module boundary of the reference) and / or store int8 NHWC.
 // A STAGES-deep smem ring (full/empty mbarriers) decouples TMA from MMA; the two TMEM accumulators
 // (tmem_full/tmem_empty mbarriers) let the epilogue of tile i overlap the main loop of tile i+1.
+// Round 2: separate A / B producer warps (warp 18 = B), 2-4 accumulator stages with one warp group per tile in
+// flight, the fused NewAdd epilogue (epilogue_add), resident weights and "patch windows" for short-K 3x3 layers
+// (GemmParams::win_*: one TMA box per tile, nine shifted descriptors), programmatic dependent launch.
 #include <cuda.h>
 #include <cstdlib>
 
