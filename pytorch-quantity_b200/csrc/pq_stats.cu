@@ -66,6 +66,20 @@ extern "C" int pq_absmax_per_channel_f32(const float *x, uint64_t outer, int cha
     if (((unsigned long long)x & 3ull) != 0) return PQ_EALIGN;
     if (channels > 8192 || inner >= (1ull << 31) - (1ull << 14) || outer * (uint64_t)channels >= (1ull << 31))
         return PQ_EUNSUPPORTED;
+    // small planes, many images: the periodic variant (one float4 column per thread, see the kernel)
+    const uint64_t per_img = (uint64_t)channels * inner;
+    if (inner < 784 && outer >= 16 && (per_img & 3) == 0 && per_img / 4 < (1ull << 31) && outer < (1ull << 31) &&
+        ((unsigned long long)x & 15ull) == 0) {
+        const unsigned int vec_per_img = (unsigned int)(per_img / 4);
+        const unsigned int gx = (vec_per_img + pq::kStatThreads - 1) / pq::kStatThreads;
+        unsigned long long gy = ((unsigned long long)pq::kNumSMs * 8 + gx - 1) / gx;        // ~8 CTAs per SM in total
+        if (gy > outer / 2) gy = outer / 2;                                               // >= 2 images per thread
+        if (gy > 65535) gy = 65535;
+        if (gy < 1) gy = 1;
+        pq::absmax_periodic_kernel<<<dim3(gx, (unsigned int)gy), pq::kStatThreads, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4 *>(x), vec_per_img, (unsigned int)outer, (unsigned int)inner, max_bits);
+        return (int)cudaGetLastError();
+    }
     pq::ChannelGeom g;
     g.total = outer * (uint64_t)channels * inner;
     g.inner = (unsigned int)inner;

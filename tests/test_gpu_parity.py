@@ -299,7 +299,10 @@ def test_abi_error_codes(cq):
 # ---------------------------------------------------------------- per-channel max-abs (extension of a1)
 CHANNEL_CASES = [((4, 64, 56, 56), 1), ((2, 1000), 1), ((3, 7, 5, 3), 1), ((1, 2048, 7, 7), 1), ((5, 3, 224, 224), 1),
                  ((2, 16, 1, 1), 1), ((64, 3, 7, 7), 0), ((512, 2048), 0), ((6, 13, 3), 1), ((1, 1, 1), 1),
-                 ((3, 8192, 2, 2), 1), ((32, 256, 56, 56), 1)]
+                 ((3, 8192, 2, 2), 1), ((32, 256, 56, 56), 1),
+                 # the periodic variant (inner < 784, >= 16 images, channels * inner % 4 == 0) and its neighbours
+                 ((64, 2048, 7, 7), 1), ((4096, 1000), 1), ((33, 12, 5, 5), 1), ((16, 8, 1, 1), 1), ((100, 6, 2), 1),
+                 ((17, 4, 3, 3), 1), ((20, 7, 3), 1), ((15, 64, 7, 7), 1), ((300, 8192), 1), ((40, 3, 28, 27), 1)]
 
 
 @pytest.mark.parametrize("shape,dim", CHANNEL_CASES, ids=["x".join(map(str, s)) + "_d%d" % d for s, d in CHANNEL_CASES])
