@@ -8,9 +8,33 @@ namespace pq {
 
 constexpr int kPipeThreads = 256;
 
+// Per-byte signed max on sm_100a: the s8x4 video instructions (__vmaxs4) are EMULATED (~9 LOP3 / PRMT / IMAD per call:
+// the ncu source view of the max-pool kernel showed 548 instructions per thread, 74 % issue utilisation at 48 % of DRAM
+// bandwidth); the s16x2 ones are hardware (VIMNMX.S16x2).  A 16-bit lane compares its HIGH byte first, so two running
+// maxima -- one over w << 8 (bytes 0 and 2 in the high halves), one over w itself (bytes 1 and 3) -- are exact in
+// their high bytes whatever the low bytes hold, and one PRMT gathers the four high bytes at the end.
+struct Max4 {
+    uint32_t e, o;                               // lanes whose high bytes are the maxima of bytes (0, 2) and (1, 3)
+};
+__device__ __forceinline__ Max4 max4_init(bool relu)
+{
+    const uint32_t v = relu ? 0u : 0x80008000u;  // 0 or -128 in every high byte
+    return Max4{v, v};
+}
+__device__ __forceinline__ void max4_acc(Max4 &m, uint32_t w)
+{
+    m.e = __vmaxs2(m.e, w << 8);
+    m.o = __vmaxs2(m.o, w);
+}
+__device__ __forceinline__ uint32_t max4_get(const Max4 &m)
+{
+    return __byte_perm(m.e, m.o, 0x7351);        // e.b1, o.b1, e.b3, o.b3
+}
 __device__ __forceinline__ uint32_t relu4_s8(uint32_t v)
 {
-    return __vmaxs4(v, 0u);                      // per-byte signed max with 0
+    Max4 m = max4_init(true);                    // per-byte signed max with 0
+    max4_acc(m, v);
+    return max4_get(m);
 }
 
 __global__ void __launch_bounds__(kPipeThreads)
@@ -46,21 +70,25 @@ maxpool_nhwc_s8_kernel(const int8_t *__restrict__ x, int8_t *__restrict__ y, int
         uint4 m = make_uint4(init, init, init, init);
         if (k == 3) {                              // the usual window: all nine loads in flight, out-of-range taps = init
             uint4 v[9];
+            const int8_t *base = xin + c16 * 16;
+            const int iy0 = pp * stride - pad, ix0 = q * stride - pad;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const int iy = pp * stride - pad + r;
-                const int8_t *row = xin + (size_t)iy * W * C + c16 * 16;
+                const int iy = iy0 + r;
+                const int row_off = iy * W * C;                       // (< 2^31: one image)
 #pragma unroll
                 for (int s = 0; s < 3; ++s) {
-                    const int ix = q * stride - pad + s;
+                    const int ix = ix0 + s;
                     v[3 * r + s] = ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
-                                       ? __ldg(reinterpret_cast<const uint4 *>(row + (size_t)ix * C)) : m;
+                                       ? __ldg(reinterpret_cast<const uint4 *>(base + row_off + ix * C)) : m;
                 }
             }
+            Max4 a = max4_init(relu != 0), b = a, c = a, d = a;
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
-                m.x = __vmaxs4(m.x, v[i].x); m.y = __vmaxs4(m.y, v[i].y); m.z = __vmaxs4(m.z, v[i].z); m.w = __vmaxs4(m.w, v[i].w);
+                max4_acc(a, v[i].x); max4_acc(b, v[i].y); max4_acc(c, v[i].z); max4_acc(d, v[i].w);
             }
+            m = make_uint4(max4_get(a), max4_get(b), max4_get(c), max4_get(d));
         } else
         for (int r = 0; r < k; ++r) {
             const int iy = pp * stride - pad + r;
