@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--fused-add", action="store_true", help="conv + NewAdd + ReLU in one kernel (int16 shortcut)")
     ap.add_argument("--classic-bias", action="store_true", help="plain int32 bias (no PQ_FLAG_BIAS_FOLDED constants)")
     ap.add_argument("--no-windows", action="store_true", help="3x3 layers through the im2col-TMA path (PQ_FLAG_NO_WINDOWS)")
+    ap.add_argument("--no-s2d", action="store_true", help="the stem on 8-byte pixels instead of the space-to-depth form")
     args = ap.parse_args()
     B = args.batch
     tot_conv = tot_q = tot_ops = 0.0
@@ -63,10 +64,27 @@ def main():
             w8 = w8.view(cout, k, 64)
             Hp = max((P - 1) * s + k, h + pad); Hp = (Hp + s - 1) // s * s
             Wp = max((P - 1) * s + 8, w + pad); Wp += Wp & 1
-            q = _native.quantize_pad_nhwc8_s8(x, 4, (pad, pad), Hp, Wp)
-            t_q = time_ms(lambda: _native.quantize_pad_nhwc8_s8(x, 4, (pad, pad), Hp, Wp))
-            t_c = time_ms(lambda: _native.conv2d_smallc_s8(q, w8, bias, (h, w), (k, k), (s, s), (pad, pad), 9, 4,
-                                                           want_f32=not args.s8_out, want_s8=args.s8_out))
+            if s == 2 and cin <= 4 and k <= 7 and not args.no_s2d:      # space-to-depth form (what NewConv2d runs)
+                e = pad & 1
+                ra = ((e + k - 1) >> 1) + 1
+                w2 = torch.zeros((cout, ra, 4, 2, 2, 4), dtype=torch.int8, device="cuda")
+                for r in range(k):
+                    a, dy = divmod(e + r, 2)
+                    for t in range(k):
+                        b, dx = divmod(e + t, 2)
+                        w2[:, a, b, dy, dx, :cin] = torch.randint(-128, 127, (cout, cin), dtype=torch.int8, device="cuda")
+                w2 = w2.view(cout, ra, 64)
+                hp2, wp2 = P + ra - 1, P + 3
+                q = _native.quantize_s2d16_s8(x, 4, (pad + e, pad + e), hp2, wp2)
+                t_q = time_ms(lambda: _native.quantize_s2d16_s8(x, 4, (pad + e, pad + e), hp2, wp2))
+                q8 = q.view(B, hp2, 2 * wp2, 8)
+                t_c = time_ms(lambda: _native.conv2d_smallc_s8(q8, w2, bias, (hp2, 2 * wp2), (ra, 8), (1, 2), (0, 0), 9, 4,
+                                                               want_f32=not args.s8_out, want_s8=args.s8_out))
+            else:
+                q = _native.quantize_pad_nhwc8_s8(x, 4, (pad, pad), Hp, Wp)
+                t_q = time_ms(lambda: _native.quantize_pad_nhwc8_s8(x, 4, (pad, pad), Hp, Wp))
+                t_c = time_ms(lambda: _native.conv2d_smallc_s8(q, w8, bias, (h, w), (k, k), (s, s), (pad, pad), 9, 4,
+                                                               want_f32=not args.s8_out, want_s8=args.s8_out))
         elif cin <= 8 and not plain:     # explicit im2col + GEMM
             kp = (k * k * cin + 63) // 64 * 64
             wn = torch.randint(-128, 127, (cout, kp), dtype=torch.int8, device="cuda")

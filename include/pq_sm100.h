@@ -210,6 +210,14 @@ int pq_conv2d_s8_dil(const int8_t *x_nhwc, const int8_t *w_krsc, const int32_t *
                      const pq_conv_desc *desc_host, int dil_h, int dil_w, int flags, float *out_f32_nchw,
                      int8_t *out_s8_nhwc, pq_stream_t stream);
 
+/* Space-to-depth form of the same input for stride-2 convolutions with C <= 4: 2 x 2 pixel blocks of the zero-padded
+ * image as 16-byte pixels, q[n][i][j][(dy * 2 + dx) * 4 + c] = Quantity(ib)(x[n][c][2i + dy - pad_t][2j + dx - pad_l])
+ * (0 outside the image / for c >= C); pad_t, pad_l even.  Viewed as [N][Hp2][2 * Wp2][8] it is a valid input of
+ * pq_conv2d_smallc_s8 for the equivalent stride-(1, 2) filter of ceil((R + 1) / 2) rows (NewConv2d builds the weights):
+ * the ResNet stem then needs 8 instead of 14 tensor-core instructions per tile and reads half the bytes. */
+int pq_quantize_nchw_to_s2d16_s8(const float *x, int8_t *q, int N, int C, int H, int W, int pad_t, int pad_l,
+                                 int Hp2, int Wp2, int ib, pq_stream_t stream);
+
 int pq_conv2d_smallc_s8(const int8_t *xp, const int8_t *w_krs8, const int32_t *bias_q,
                         const pq_conv_desc *desc_host, int Hp, int Wp, int flags, float *out_f32_nchw,
                         int8_t *out_s8_nhwc, pq_stream_t stream);

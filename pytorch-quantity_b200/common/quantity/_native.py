@@ -41,6 +41,7 @@ SYMBOLS = {
     "pq_quantize_im2col_s8": (_i, [_vp, _vp] + [_i] * 12 + [_vp]),
     "pq_quantize_nchw_to_padded_nhwc8_s8": (_i, [_vp, _vp] + [_i] * 9 + [_vp]),
     "pq_conv2d_smallc_s8": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "pq_quantize_nchw_to_s2d16_s8": (_i, [_vp, _vp] + [_i] * 9 + [_vp]),
     "pq_gemm_s8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pq_conv2d_s8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pq_gemm_s8_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -340,8 +341,22 @@ def quantize_pad_nhwc8_s8(x, ib, padding, Hp, Wp):
     return q
 
 
+def quantize_s2d16_s8(x, ib, pad_tl, Hp2, Wp2):
+    """fp32 NCHW (C <= 4) -> int8 [N][Hp2][Wp2][16]: 2 x 2 blocks of the zero-padded image (even pad_tl) as 16-byte
+    pixels, the input of the space-to-depth form of a stride-2 small-channel convolution."""
+    require_cuda(x, "quantize_s2d16_s8")
+    assert x.dim() == 4 and x.dtype == torch.float32
+    xc = x.contiguous()
+    N, C, H, W = xc.shape
+    q = torch.empty((N, Hp2, Wp2, 16), dtype=torch.int8, device=x.device)
+    with _Timed("quantize_s8", 1, xc.numel() * 4 + q.numel(), xc.device):
+        check(lib().pq_quantize_nchw_to_s2d16_s8(xc.data_ptr(), q.data_ptr(), N, C, H, W, pad_tl[0], pad_tl[1], Hp2, Wp2,
+                                                 int(ib), _stream(xc)), "pq_quantize_nchw_to_s2d16_s8")
+    return q
+
+
 def conv2d_smallc_s8(xp, w_krs8, bias_q, in_hw, kernel, stride, padding, rs, ob, want_f32=True, want_s8=False,
-                     c_real=None, relu=False):
+                     c_real=None, relu=False, ops=None):
     """xp int8 [N][Hp][Wp][8] (padded), w_krs8 int8 [K][R][64] -> fp32 NCHW and / or int8 NHWC."""
     require_cuda(xp, "conv2d_smallc_s8")
     N, Hp, Wp, _ = xp.shape
@@ -353,7 +368,7 @@ def conv2d_smallc_s8(xp, w_krs8, bias_q, in_hw, kernel, stride, padding, rs, ob,
     d = ConvDesc(N, H, W, 8, K, R, S, stride[0], stride[1], padding[0], padding[1], P, Q, int(rs), int(ob))
     out_f32 = torch.empty((N, K, P, Q), dtype=torch.float32, device=xp.device) if want_f32 else None
     out_s8 = torch.empty((N, P, Q, K), dtype=torch.int8, device=xp.device) if want_s8 else None
-    with _Timed("conv_s8", 1, 2 * N * P * Q * K * R * S * (c_real or 8), xp.device):        # int8 ops
+    with _Timed("conv_s8", 1, ops or 2 * N * P * Q * K * R * S * (c_real or 8), xp.device):        # int8 ops
         check(lib().pq_conv2d_smallc_s8(xp.data_ptr(), w_krs8.data_ptr(), bias_q.data_ptr(), ctypes.byref(d), Hp, Wp,
                                         _bias_flags(bias_q, K, relu), out_f32.data_ptr() if want_f32 else None,
                                         out_s8.data_ptr() if want_s8 else None, _stream(xp)), "pq_conv2d_smallc_s8")

@@ -40,6 +40,7 @@ WRITE_DIAGNOSTICS = False
 # re-evaluate their accumulator exactly (float64, slow) on every forward, keep ``max_abs_acc`` on the module and
 # warn when it reaches 2^24, so that such a mismatch is explained rather than mysterious.
 CHECK_ACC_RANGE = False
+S2D_STEM = True            # stride-2 convolutions with <= 4 input channels in space-to-depth form (A/B switch)
 FP32_EXACT_LIMIT = 1 << 24
 
 
@@ -218,6 +219,22 @@ class NewConv2d(_IntSimBase):
             w = torch.zeros((K, R, 8, 8), dtype=torch.int8, device=wq.device)       # [K][R][tap slot][channel slot]
             w[:, :, :S, :C] = wq.permute(0, 2, 3, 1).to(torch.int8)
             self.register_buffer("_w_krs8", w.view(K, R, 64).contiguous())
+            # Stride 2 with <= 4 channels (the ResNet stem): space-to-depth form.  2 x 2 blocks of the padded image
+            # become 16-byte pixels (pq_quantize_nchw_to_s2d16_s8), the R x S / stride-2 filter a ceil((R + 1) / 2)-row
+            # stride-1 filter over them: tap (r, s) sits in block (a, b), phase (dy, dx) with
+            # (a, dy) = divmod(r + e_h, 2), e_h = padding parity (the padded image starts on an even row).  Same
+            # 64-byte row window, rows 16 bytes apart -> the same kernel, 8 instead of 14 MMAs per tile for 7 x 7.
+            self._s2d = S2D_STEM and tuple(conv.stride) == (2, 2) and C <= 4 and R <= 7 and S <= 7
+            if self._s2d:
+                eh, ew = conv.padding[0] & 1, conv.padding[1] & 1
+                ra = ((eh + R - 1) >> 1) + 1
+                w2 = torch.zeros((K, ra, 4, 2, 2, 4), dtype=torch.int8, device=wq.device)   # [K][a][b][dy][dx][c]
+                for r in range(R):
+                    a, dy = divmod(eh + r, 2)
+                    for t in range(S):
+                        b, dx = divmod(ew + t, 2)
+                        w2[:, a, b, dy, dx, :C] = wq[:, :, r, t].to(torch.int8)
+                self.register_buffer("_w_s2d", w2.view(K, ra, 64).contiguous(), persistent=False)
             return
         if self._explicit_im2col:
             self._k_pad = (R * S * C + 63) // 64 * 64
@@ -285,6 +302,15 @@ class NewConv2d(_IntSimBase):
         (R, S), (sh, sw), (ph, pw) = conv.kernel_size, conv.stride, conv.padding
         H, W = input.shape[2], input.shape[3]
         P, Q = (H + 2 * ph - R) // sh + 1, (W + 2 * pw - S) // sw + 1
+        if getattr(self, "_s2d", False):
+            ra = self._w_s2d.shape[1]
+            hp2, wp2 = P + ra - 1, Q + 3                       # blocks the 64-byte row windows of every output touch
+            xs = _native.quantize_s2d16_s8(input, self.input_bit, (ph + (ph & 1), pw + (pw & 1)), hp2, wp2)
+            # the same bytes as an 8-byte-pixel image of twice the width: filter of ra rows x 8 slots, stride (1, 2)
+            return _native.conv2d_smallc_s8(xs.view(xs.shape[0], hp2, 2 * wp2, 8), self._w_s2d, self._bias_i32,
+                                            (hp2, 2 * wp2), (ra, 8), (1, 2), (0, 0), self.rs_bit, self.output_bit,
+                                            want_f32=want_f32, want_s8=want_s8, relu=relu,
+                                            ops=2 * input.shape[0] * P * Q * conv.out_channels * R * S * conv.in_channels)
         Hp = max((P - 1) * sh + R, H + ph)
         Hp = (Hp + sh - 1) // sh * sh
         Wp = max((Q - 1) * sw + 8, W + pw)

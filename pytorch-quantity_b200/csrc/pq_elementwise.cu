@@ -343,6 +343,65 @@ quantize_pad_nhwc8_v4_kernel(const float *__restrict__ x, uint2 *__restrict__ q,
     }
 }
 
+// Space-to-depth input quantiser for stride-2 small-channel convolutions (C <= 4): the zero-padded image is cut into
+// 2 x 2 pixel blocks and every block becomes ONE 16-byte pixel  q[n][i][j][(dy * 2 + dx) * 4 + c] =
+// q(x[n][c][2i + dy - pad_t][2j + dx - pad_l])  (0 outside the image and for c >= C).  A 7 x 7 / stride 2 filter is
+// then a 4 x 4 / stride 1 filter over 16-byte pixels: its row window is the same 64 bytes, consecutive output columns
+// are the same 16 bytes apart (so pq_conv2d_smallc_s8's row kernel runs on it unchanged, see NewConv2d), but it has
+// 4 filter rows instead of 7 (8 narrow MMAs per tile instead of 14) and the tensor is half as large (12 of 16 bytes
+// carry data instead of 3 of 8).  One thread per block: two rows x C channels of float2 loads, one 16-byte store.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+quantize_s2d16_kernel(const float *__restrict__ x, uint4 *__restrict__ q, int C, int H, int W, int pad_t, int pad_l,
+                      int Hp2, int Wp2, float scale)
+{
+    const int item = blockIdx.x * 256 + threadIdx.x;
+    if (item >= Hp2 * Wp2) return;
+    const size_t n = blockIdx.y;
+    const int i = item / Wp2, j = item - i * Wp2;
+    const int w0 = 2 * j - pad_l;
+    const size_t HW = (size_t)H * W;
+    // every load is issued before the first conversion (predicated, no control flow in between)
+    float2 v[2][4];
+    const bool both = w0 >= 0 && w0 + 1 < W;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const int h = 2 * i + dy - pad_t;
+        const bool rok = (unsigned)h < (unsigned)H;
+        const float *row = x + (n * C * H + (rok ? h : 0)) * (size_t)W + (both ? w0 : 0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            v[dy][c] = make_float2(0.0f, 0.0f);
+            if (VEC) {
+                if (rok && both && c < C) v[dy][c] = __ldg(reinterpret_cast<const float2 *>(row + c * HW));
+            }
+        }
+    }
+    if (!VEC || !both) {                                   // image border / unaligned rows: scalar loads
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const int h = 2 * i + dy - pad_t;
+            if ((unsigned)h >= (unsigned)H) continue;
+            const float *row = x + (n * C * H + h) * (size_t)W;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < C && (unsigned)w0 < (unsigned)W) v[dy][c].x = __ldg(row + c * HW + w0);
+                if (c < C && (unsigned)(w0 + 1) < (unsigned)W) v[dy][c].y = __ldg(row + c * HW + w0 + 1);
+            }
+        }
+    }
+    unsigned int word[4] = {0u, 0u, 0u, 0u};               // one word per phase (dy, dx): bytes = channels
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            // (channels >= C and rows / columns outside the image hold 0.0f: q8i(0) == 0)
+            word[2 * dy] |= ((unsigned int)q8i(v[dy][c].x, scale) & 0xffu) << (c * 8);
+            word[2 * dy + 1] |= ((unsigned int)q8i(v[dy][c].y, scale) & 0xffu) << (c * 8);
+        }
+    q[n * (size_t)Hp2 * Wp2 + item] = make_uint4(word[0], word[1], word[2], word[3]);
+}
+
 __global__ void __launch_bounds__(kEwThreads)
 quantize_pad_nhwc8_kernel(const float *__restrict__ x, uint2 *__restrict__ q, int C, int H, int W, int ph, int pw,
                           int Hp, int Wp, float scale)
@@ -502,5 +561,24 @@ extern "C" int pq_quantize_nchw_to_padded_nhwc8_s8(const float *x, int8_t *q, in
     }
     pq::quantize_pad_nhwc8_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
         x, reinterpret_cast<uint2 *>(q), C, H, W, pad_h, pad_w, Hp, Wp, ldexpf(1.0f, ib));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pq_quantize_nchw_to_s2d16_s8(const float *x, int8_t *q, int N, int C, int H, int W, int pad_t, int pad_l,
+                                            int Hp2, int Wp2, int ib, pq_stream_t stream)
+{
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || pad_t < 0 || pad_l < 0 || Hp2 <= 0 || Wp2 <= 0 || !x || !q) return PQ_EINVAL;
+    if (C > 4 || (pad_t & 1) || (pad_l & 1) || ib < -126 || ib > 126 || N > 65535) return PQ_EUNSUPPORTED;
+    if ((long long)Hp2 * Wp2 > 0x7fffffffLL) return PQ_EUNSUPPORTED;
+    if (!aligned16(q) || (((unsigned long long)x) & 3ull)) return PQ_EALIGN;
+    const dim3 grid((unsigned)(((long long)Hp2 * Wp2 + 255) / 256), (unsigned)N);
+    const float scale = ldexpf(1.0f, ib);
+    // float2 loads need every row start 8-byte aligned: even W and an 8-byte aligned tensor
+    if ((W & 1) == 0 && (((unsigned long long)x) & 7ull) == 0)
+        pq::quantize_s2d16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            x, reinterpret_cast<uint4 *>(q), C, H, W, pad_t, pad_l, Hp2, Wp2, scale);
+    else
+        pq::quantize_s2d16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            x, reinterpret_cast<uint4 *>(q), C, H, W, pad_t, pad_l, Hp2, Wp2, scale);
     return (int)cudaGetLastError();
 }

@@ -100,9 +100,12 @@ SMALLC_SHAPES = [(2, 3, 64, 64, 64, 7, 2, 3), (3, 3, 37, 53, 32, 7, 2, 3), (1, 1
                  (2, 3, 33, 41, 32, 7, 4, 3), (1, 3, 40, 300, 72, 3, 2, 1)]
 
 
-@pytest.mark.parametrize("shape", SMALLC_SHAPES, ids=["b%d_c%d_%dx%d_o%d_k%d_s%d" % s[:7] for s in SMALLC_SHAPES])
+@pytest.mark.parametrize("shape", SMALLC_SHAPES + [(2, 3, 35, 29, 32, 3, 2, 1), (2, 2, 16, 16, 16, 2, 2, 0),
+                                                  (1, 4, 31, 40, 64, 5, 2, 2), (2, 3, 26, 22, 48, 7, 2, 2)],
+                         ids=lambda s: "b%d_c%d_%dx%d_o%d_k%d_s%d" % s[:7])
 @pytest.mark.parametrize("relu", [False, True])
-def test_smallc_conv_vs_oracle_and_im2col(oracle, shape, relu):
+@pytest.mark.parametrize("s2d", [True, False], ids=["s2d", "rows8"])
+def test_smallc_conv_vs_oracle_and_im2col(oracle, shape, relu, s2d):
     """pq_quantize_nchw_to_padded_nhwc8_s8 + pq_conv2d_smallc_s8 (overlapping-window TMA) against the oracle's
     integer conv layer and against the explicit-im2col GEMM path, fp32 NCHW and int8 NHWC outputs."""
     import common.quantity as cq
@@ -117,6 +120,10 @@ def test_smallc_conv_vs_oracle_and_im2col(oracle, shape, relu):
         conv.weight.copy_(torch.from_numpy(w)); conv.bias.copy_(torch.from_numpy(b))
         m = cq.NewConv2d(conv.cuda(), dict(info))
         assert m._smallc
+        # stride (2, 2) with <= 4 channels takes the space-to-depth form by default; both forms must agree
+        if s2d and not m._s2d:
+            pytest.skip("not a space-to-depth shape")
+        m._s2d = s2d
         f32, s8 = m._smallc_forward(dev(x), want_f32=True, want_s8=True, relu=relu)
     ref, _ = oracle.int_conv_layer(x, w, b, info, stride=stride, padding=pad)
     if relu:
