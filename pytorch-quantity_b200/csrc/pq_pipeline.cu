@@ -124,14 +124,20 @@ avgpool_global_kernel(const void *__restrict__ x, float *__restrict__ out, int H
     int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (IS16) {
         const int16_t *p = reinterpret_cast<const int16_t *>(x) + n * (size_t)HW * C + c0;
-        for (int i = 0; i < HW; ++i, p += C) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(p);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int i0 = 0; i0 < HW; i0 += 8) {                 // eight pixels in flight (a 7 x 7 plane is 49 dependent loads otherwise)
+            uint4 v[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int lo = (int)(short)(w[j] & 0xffffu), hi = (int)w[j] >> 16;
-                if (relu) { lo = max(lo, 0); hi = max(hi, 0); }
-                acc[2 * j] += lo; acc[2 * j + 1] += hi;
+            for (int u = 0; u < 8; ++u)
+                v[u] = i0 + u < HW ? __ldg(reinterpret_cast<const uint4 *>(p + (size_t)(i0 + u) * C)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int lo = (int)(short)(w[j] & 0xffffu), hi = (int)w[j] >> 16;
+                    if (relu) { lo = max(lo, 0); hi = max(hi, 0); }
+                    acc[2 * j] += lo; acc[2 * j + 1] += hi;
+                }
             }
         }
     } else {
