@@ -226,15 +226,7 @@ class NewConv2d(_IntSimBase):
             # 64-byte row window, rows 16 bytes apart -> the same kernel, 8 instead of 14 MMAs per tile for 7 x 7.
             self._s2d = S2D_STEM and tuple(conv.stride) == (2, 2) and C <= 4 and R <= 7 and S <= 7
             if self._s2d:
-                eh, ew = conv.padding[0] & 1, conv.padding[1] & 1
-                ra = ((eh + R - 1) >> 1) + 1
-                w2 = torch.zeros((K, ra, 4, 2, 2, 4), dtype=torch.int8, device=wq.device)   # [K][a][b][dy][dx][c]
-                for r in range(R):
-                    a, dy = divmod(eh + r, 2)
-                    for t in range(S):
-                        b, dx = divmod(ew + t, 2)
-                        w2[:, a, b, dy, dx, :C] = wq[:, :, r, t].to(torch.int8)
-                self.register_buffer("_w_s2d", w2.view(K, ra, 64).contiguous(), persistent=False)
+                self.register_buffer("_w_s2d", s2d_filter(wq, conv.padding), persistent=False)
             return
         if self._explicit_im2col:
             self._k_pad = (R * S * C + 63) // 64 * 64
@@ -319,6 +311,24 @@ class NewConv2d(_IntSimBase):
         return _native.conv2d_smallc_s8(xp, self._w_krs8, self._bias_i32, (H, W), (R, S), (sh, sw), (ph, pw),
                                         self.rs_bit, self.output_bit, want_f32=want_f32, want_s8=want_s8,
                                         c_real=conv.in_channels, relu=relu)
+
+
+def s2d_filter(wq, padding):
+    """Integer filter [K][C <= 4][R <= 7][S <= 7] of a stride-2 convolution -> int8 [K][ra][64]: the equivalent stride-1
+    filter over the space-to-depth image of pq_quantize_nchw_to_s2d16_s8 (16-byte pixels = 2 x 2 blocks, byte
+    (dy * 2 + dx) * 4 + c), ra = ceil((R + e_h) / 2) rows of four blocks each.  The padded image starts on an even row /
+    column (pad rounded up to even, e = pad & 1), so tap (r, s) lies in block (a, b), phase (dy, dx) with
+    (a, dy) = divmod(r + e_h, 2), (b, dx) = divmod(s + e_w, 2)."""
+    K, C, R, S = wq.shape
+    eh, ew = int(padding[0]) & 1, int(padding[1]) & 1
+    ra = ((eh + R - 1) >> 1) + 1
+    w2 = torch.zeros((K, ra, 4, 2, 2, 4), dtype=torch.int8, device=wq.device)       # [K][a][b][dy][dx][c]
+    for r in range(R):
+        a, dy = divmod(eh + r, 2)
+        for t in range(S):
+            b, dx = divmod(ew + t, 2)
+            w2[:, a, b, dy, dx, :C] = wq[:, :, r, t].to(torch.int8)
+    return w2.view(K, ra, 64).contiguous()
 
 
 class NewLinear(_IntSimBase):

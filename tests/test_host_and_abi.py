@@ -200,3 +200,51 @@ def test_tools_surface_matches_the_reference():
     for m in ("ReconModel", "ReconTest"):               # reconstruction.py:175, :243
         assert list(inspect.signature(getattr(tools.Reconstruction, m)).parameters) == \
             ["self", "all_quantize_infor", "new_model_path"], m
+
+
+def test_space_to_depth_filter_mapping_equals_stride2_convolution():
+    """new_quantity_op.s2d_filter + the layout of pq_quantize_nchw_to_s2d16_s8, emulated in torch on the CPU: the
+    stride-1 filter over 16-byte space-to-depth pixels must reproduce the stride-2 convolution (odd sizes, odd / even /
+    zero padding, 1-4 channels, non-square filters)."""
+    import torch
+    import torch.nn.functional as F
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "_nqo_src", os.path.join(os.path.dirname(__file__), "..", "pytorch-quantity_b200", "common", "quantity",
+                                 "new_quantity_op.py"))
+    src = open(spec.origin).read()
+    ns = {"torch": torch}
+    start = src.index("def s2d_filter(")
+    exec(src[start:src.index("class NewLinear(")], ns)           # the pure-torch helper, without importing the CUDA package
+    s2d_filter = ns["s2d_filter"]
+    g = torch.Generator().manual_seed(0)
+    for (C, H, W, K, R, S, ph, pw) in [(3, 20, 20, 4, 7, 7, 3, 3), (3, 13, 17, 5, 7, 7, 3, 3), (1, 12, 12, 3, 3, 3, 1, 1),
+                                       (4, 10, 9, 2, 5, 5, 2, 2), (3, 11, 14, 2, 3, 3, 0, 0), (2, 9, 9, 3, 7, 5, 3, 2),
+                                       (3, 16, 16, 2, 2, 2, 0, 0), (3, 15, 12, 2, 6, 4, 2, 1)]:
+        x = torch.randint(-128, 128, (2, C, H, W), generator=g).double()
+        w = torch.randint(-128, 128, (K, C, R, S), generator=g).double()
+        ref = F.conv2d(x, w, stride=2, padding=(ph, pw))
+        P, Q = ref.shape[2], ref.shape[3]
+        w2 = s2d_filter(w, (ph, pw)).double()
+        ra = w2.shape[1]
+        pt, pl = ph + (ph & 1), pw + (pw & 1)
+        hp2, wp2 = P + ra - 1, Q + 3
+        xs = torch.zeros(2, hp2, wp2, 2, 2, 4, dtype=torch.float64)
+        for i in range(hp2):
+            for dy in range(2):
+                h = 2 * i + dy - pt
+                if not 0 <= h < H:
+                    continue
+                for j in range(wp2):
+                    for dx in range(2):
+                        ww = 2 * j + dx - pl
+                        if 0 <= ww < W:
+                            xs[:, i, j, dy, dx, :C] = x[:, :, h, ww]
+        xs = xs.view(2, hp2, wp2 * 16)
+        out = torch.zeros_like(ref)
+        for p in range(P):
+            for q in range(Q):
+                for a in range(ra):
+                    out[:, :, p, q] += xs[:, p + a, q * 16:q * 16 + 64] @ w2[:, a, :].T
+        assert torch.equal(out, ref), (C, H, W, K, R, S, ph, pw)
