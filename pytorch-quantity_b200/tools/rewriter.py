@@ -12,7 +12,7 @@ import numpy as np
 
 from common.quantity import BitReader, walk_dirs
 
-from ._jsonio import dump_int_array
+from ._jsonio import dump_int_array, written_array
 
 
 def _rescale(values, old_bit, new_bit):
@@ -46,8 +46,10 @@ class BiasReWriter:
             if layer not in new_bits:
                 print("Can't find {} in weight table, but json file exists.".format(layer))
                 continue
-            with open(path, "r") as f:
-                values = json.load(f)
+            values = written_array(path)                   # ours, unchanged since we wrote it: no need to parse it
+            if values is None:
+                with open(path, "r") as f:
+                    values = json.load(f)
             dump_int_array(_rescale(values, old_bits[layer], new_bits[layer]),
                            osp.join(dst_dir, osp.basename(path)))
 

@@ -248,3 +248,24 @@ def test_space_to_depth_filter_mapping_equals_stride2_convolution():
                 for a in range(ra):
                     out[:, :, p, q] += xs[:, p + a, q * 16:q * 16 + 64] @ w2[:, a, :].T
         assert torch.equal(out, ref), (C, H, W, K, R, S, ph, pw)
+
+
+def test_rewriter_reuses_arrays_it_wrote_and_reparses_foreign_files(tmp_path):
+    """tools/_jsonio.written_array: the array behind a file this process wrote is reused only while the file is
+    unchanged; a file modified (or written) by somebody else is parsed again."""
+    import time
+    from tools._jsonio import dump_int_array, written_array
+    p = str(tmp_path / "w.json")
+    a = np.arange(-6, 6, dtype=np.int32).reshape(3, 4)
+    dump_int_array(a, p)
+    got = written_array(p)
+    assert got is not None and np.array_equal(got, a) and got is not a
+    assert np.array_equal(np.array(json.load(open(p))), a)
+    time.sleep(0.01)
+    with open(p, "w") as f:                                  # same size, other content, later mtime
+        f.write(open(p).read().replace("5", "4"))
+    assert written_array(p) is None
+    assert written_array(str(tmp_path / "missing.json")) is None
+    q = str(tmp_path / "foreign.json")
+    json.dump(a.tolist(), open(q, "w"), indent=4)
+    assert written_array(q) is None
